@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the geodesic-guidance hot path (BASELINE.json metric: geodesic maps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One step = one pass of the hot path (FPS seeds -> kNN graph -> geodesic maps) over one synthetic
+scene of the workload (default c2: 100k points, 256 seeds, k=16, radius 0.5, 32 levels).
+  value     whole-job maps/s with the scenes already resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the host-buffer C-ABI call gf_guidance_host: pinned host points in,
+            seeds + maps back in pinned host memory, copies inside the timed region
+  roofline  the level kernel (geo_levels_kernel): algorithmic bytes of SURVEY 8(d) / its live
+            CUDA-event duration, against the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle port (oracle/) on this box's host cores, bounded sample (N=1 only)
+--impl reference times that CPU port as the reference arm (the reference's own torch code cannot
+travel to the GPU box and its kNN is faiss-gpu, absent everywhere).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
+    ap.add_argument("--max-step", type=int, default=None, help="override the workload's level bound")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from geoformer_b200.scenes import CONFIGS
+
+    cfg = dict(CONFIGS[args.workload])
+    if args.max_step is not None:
+        cfg["max_step"] = args.max_step
+    return cfg
+
+
+def make_scene(cfg, index):
+    from geoformer_b200 import scenes
+
+    gen = scenes.scene if cfg["gen"] == "scene" else scenes.room
+    return gen(cfg["n"], cfg["seed"] + index)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """per-launch DRAM bytes of the level kernel from the committed ncu capture, if any"""
+    p = os.path.join(ROOT, "profiles", "geo_levels_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if bit and (r & bit):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port (oracle) timing: used for cpu_baseline and for --impl reference.  The ONLY place bench.py
+# touches oracle/.
+# ------------------------------------------------------------------------------------------------
+class CpuPort:
+    def __init__(self, cfg, budget_s):
+        import numpy as np
+
+        import oracle
+
+        oracle.build()
+        self.np, self.oracle, self.cfg = np, oracle, cfg
+        self.x = make_scene(cfg, 0).numpy()
+        self.N, self.Q, self.k = cfg["n"], cfg["Q"], cfg["k"]
+        self.cores = oracle.num_threads()
+        # probe the kNN rate on a small row sample, then size the per-step sample to the budget
+        rows = min(self.N, 1024)
+        t0 = time.perf_counter()
+        oracle.knn_sq(self.x, self.k, self.x[:rows])
+        rate = (time.perf_counter() - t0) / rows  # seconds per query row
+        t0 = time.perf_counter()
+        self.seeds = oracle.furthest_point_sampling(self.x[None], self.Q)[0]
+        self.t_fps_probe = time.perf_counter() - t0
+        knn_budget = max(0.2, budget_s - self.t_fps_probe - 0.3)
+        self.rows = int(min(self.N, max(1024, knn_budget / max(rate, 1e-9))))
+        self.full = self.rows >= self.N
+        # the propagation needs the whole graph; when the kNN is sampled it is built once, untimed
+        self.D, self.I = oracle.find_knn(self.x, self.k)
+        self.sample = ("full scene per step" if self.full else
+                       "per step: FPS full + kNN on %d of %d query rows (time scaled x%.2f) + geodesic full, "
+                       "graph for the propagation prebuilt untimed" % (self.rows, self.N, self.N / self.rows))
+
+    def step(self):
+        """returns the (extrapolated) seconds one full scene takes on the host cores"""
+        o, np = self.oracle, self.np
+        t0 = time.perf_counter()
+        seeds = o.furthest_point_sampling(self.x[None], self.Q)[0]
+        t1 = time.perf_counter()
+        if self.full:
+            D2, I = o.knn_sq(self.x, self.k)
+            D = np.sqrt(D2)
+        else:
+            o.knn_sq(self.x, self.k, self.x[: self.rows])
+            D, I = self.D, self.I
+        t2 = time.perf_counter()
+        o.geodesic(D, I, seeds, self.cfg["radius"], self.cfg["max_step"])
+        t3 = time.perf_counter()
+        t_knn = (t2 - t1) * (1.0 if self.full else self.N / self.rows)
+        return (t1 - t0) + t_knn + (t3 - t2), {"fps_s": t1 - t0, "knn_s": t_knn, "geodesic_s": t3 - t2}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = workload(args)
+    budget = min(3.0, 150.0 / max(1, args.steps + args.warmup))
+    port = CpuPort(cfg, budget)
+    for _ in range(args.warmup):
+        port.step()
+    t_wall0 = time.perf_counter()
+    total, parts = 0.0, []
+    for _ in range(args.steps):
+        t, p = port.step()
+        total += t
+        parts.append(p)
+    wall = time.perf_counter() - t_wall0
+    ms = 1e3 * total / max(1, args.steps)
+    value = cfg["Q"] / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": "geodesic maps/sec", "value": value, "unit": "maps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_block(cfg, args, extra={"arm": "CPU port of the reference path (oracle/oracle.c, OpenMP)"}),
+        "cpu_baseline": {"value": value, "unit": "maps/s", "cores": port.cores, "kind": "port", "sample": port.sample},
+        "e2e": {"value": value, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stage_s": {k: statistics.mean(p[k] for p in parts) for k in parts[0]} if parts else {},
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def config_block(cfg, args, extra=None):
+    c = {"workload": "%s: %s(n=%d), Q=%d seeds, k=%d, radius=%.3g, max_step=%d" % (
+        args.workload, cfg["gen"], cfg["n"], cfg["Q"], cfg["k"], cfg["radius"], cfg["max_step"]),
+        "N": cfg["n"], "Q": cfg["Q"], "k": cfg["k"], "radius": cfg["radius"], "max_step": cfg["max_step"]}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    from geoformer_b200 import _capi as C
+    from geoformer_b200.guidance import GuidanceRunner, HostGuidance
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = workload(args)
+    N, Q, k = cfg["n"], cfg["Q"], cfg["k"]
+    L = C.lib()
+    # rotating scenes: per-scene footprint (points + workspace + maps) x S is far above the 126 MB L2
+    per_scene = L.gf_guidance_workspace_bytes(N, Q, k) + 4 * Q * N + 12 * N
+    S = int(max(2, min(8, (6 << 30) // max(per_scene, 1))))
+    scenes_host = [make_scene(cfg, rank * 8 + s) for s in range(S)]
+    xs = [x.to(dev) for x in scenes_host]
+    runners = [GuidanceRunner(N, Q, k, cfg["radius"], cfg["max_step"], device=dev) for _ in range(S)]
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(3, args.warmup)):
+        runners[i % S].run(xs[i % S])
+    torch.cuda.synchronize(dev)
+    reach = [int(r.stats[0].item()) for r in runners[: min(S, max(3, args.warmup))]]
+    levels = [int(r.stats[1].item()) for r in runners[: min(S, max(3, args.warmup))]]
+
+    # ---- device-resident timed region -----------------------------------------------------------
+    K = args.steps
+    ev = [[L.gf_event_create() for _ in range(5)] for _ in range(K)]
+    ev_arr = [(ctypes.c_void_p * 5)(*e) for e in ev]
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    C.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        L.gf_set_stage_events(ev_arr[i], 5)
+        runners[i % S].run(xs[i % S], stream)
+    e1.record(stream)
+    barrier()
+    launches = C.launch_count()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * K * Q / (ms_total * 1e-3)
+
+    def stage(a, b):
+        v = [L.gf_event_elapsed_ms(e[a], e[b]) for e in ev]
+        v = [x for x in v if x >= 0]
+        return statistics.mean(v) if v else None
+
+    stage_ms = {"knn_grid_build": stage(0, 1), "knn_query_and_fps_join": stage(1, 2), "geodesic_csr_and_fill": stage(2, 3),
+                "geodesic_levels": stage(3, 4), "whole_call": stage(0, 4)}
+    for e in ev:
+        for h in e:
+            L.gf_event_destroy(h)
+
+    # ---- roofline of the level kernel -------------------------------------------------------------
+    Kn = k - 1
+    R = statistics.mean(reach) if reach else 0
+    b_geo = 4.0 * Q * N + (R + Q) * Kn * 12.0 + 4.0 * R  # per reached pair 12K+4 B, + dense output
+    peak, peak_src = measured_peak()
+    t_lv = stage_ms["geodesic_levels"]
+    achieved = (b_geo / (t_lv * 1e-3)) / 1e9 if t_lv else None
+    roofline = {"bound": "hbm", "kernel": "geo_levels_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_geo, "reached_pairs_R": R, "levels": max(levels) if levels else None,
+                "kernel_ms": t_lv,
+                "compulsory_bytes": 12.0 * N + 8.0 * N * k + 4.0 * Q * N}
+
+    # ---- end to end through the host-buffer C-ABI call ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pinned = [x.pin_memory() for x in scenes_host]
+        nthreads = 2
+        hgs = [HostGuidance(N, Q, k, cfg["radius"], cfg["max_step"], device=dev) for _ in range(nthreads)]
+        Ke = max(4, min(K, 32))
+        for h in hgs:
+            h.run(pinned[0])
+
+        def worker(tid):
+            torch.cuda.set_device(local)
+            for i in range(tid, Ke, nthreads):
+                hgs[tid].run(pinned[i % S])
+
+        barrier()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * Ke * Q / dt, "unit": "maps/s", "h2d_bytes_per_step": hgs[0].h2d_bytes,
+               "d2h_bytes_per_step": hgs[0].d2h_bytes, "steps": Ke, "ms_per_step": 1e3 * dt / Ke,
+               "call": "gf_guidance_host (pinned host buffers, %d overlapped host threads)" % nthreads}
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            port = CpuPort(cfg, budget_s=6.0)
+            ts = [port.step()[0] for _ in range(2)]
+            cpu = {"value": Q / min(ts), "unit": "maps/s", "cores": port.cores, "kind": "port", "sample": port.sample}
+        except Exception as ex:  # the benchmark itself must not depend on the checker
+            cpu = {"value": None, "unit": "maps/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        line = {
+            "metric": "geodesic maps/sec", "value": value, "unit": "maps/s", "n_gpus": world, "steps": K,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_block(cfg, args, extra={
+                "parallelism": "scene-parallel x%d (one scene per rank per step, no collective)" % world,
+                "l2": "%d rotating scenes per rank, %.0f MB footprint each (> 126 MB L2 in total)" % (S, per_scene / 1e6)}),
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "stage_ms": stage_ms, "scenes_per_s": value / Q,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))

@@ -1,0 +1,135 @@
+"""ctypes binding of libgeoformer_b200.so (include/geoformer_b200.h).
+
+This is the only place the shared library is loaded.  There is NO fallback: if the library is
+missing or a tensor is not on a CUDA device the call raises RuntimeError (the reference raises
+through AT_ASSERT "CPU not supported", sampling.cpp:35-37).
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgeoformer_b200.so")
+
+_lib = None
+_lock = threading.Lock()
+
+c_int, c_float, c_size_t, c_void_p, c_int64 = ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int64
+
+# name -> (restype, argtypes); mirrors include/geoformer_b200.h one to one
+_P = c_void_p
+SIGNATURES = {
+    "gf_last_error": (ctypes.c_char_p, []),
+    "gf_version": (c_int, []),
+    "gf_launch_count": (c_int64, []),
+    "gf_reset_launch_count": (None, []),
+    "gf_set_stage_events": (c_int, [_P, c_int]),
+    "gf_event_create": (c_void_p, []),
+    "gf_event_destroy": (None, [_P]),
+    "gf_event_elapsed_ms": (c_float, [_P, _P]),
+    "gf_fps_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gf_furthest_point_sampling": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "gf_gather_points": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "gf_gather_points_grad": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "gf_ball_query": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P]),
+    "gf_group_points": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "gf_group_points_grad": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "gf_three_nn": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "gf_three_interpolate": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "gf_three_interpolate_grad": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "gf_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "gf_knn": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_size_t, _P]),
+    "gf_geodesic_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gf_geodesic": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gf_bias_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gf_bias_decoder": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "gf_bias_mask_head": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, c_size_t, _P]),
+    "gf_guidance_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gf_guidance": (c_int, [_P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gf_guidance_seeded": (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gf_guidance_host_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gf_guidance_host": (c_int, [_P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
+}
+
+
+def lib():
+    """Load the CUDA library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        "geoformer_b200: %s is missing; build it with `python -m geoformer_b200.build` "
+                        "(there is no CPU or PyTorch fallback)" % LIB_PATH)
+                h = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(h, name)  # AttributeError = header / library mismatch
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = h
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().gf_last_error()
+        raise RuntimeError("%s failed (status %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def launch_count():
+    return int(lib().gf_launch_count())
+
+
+def reset_launch_count():
+    lib().gf_reset_launch_count()
+
+
+# ---- tensor plumbing ------------------------------------------------------------------------------
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def stream_of(device):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require(cond, msg):
+    # the reference's AT_ASSERT surfaces in Python as RuntimeError (utils.h:8-28)
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def check_cuda_f32(x, name):
+    require(isinstance(x, torch.Tensor), "%s must be a tensor" % name)
+    require(x.is_cuda, "%s: CPU not supported (must be a CUDA tensor)" % name)
+    require(x.is_contiguous(), "%s must be a contiguous tensor" % name)
+    require(x.dtype == torch.float32, "%s must be a float tensor" % name)
+
+
+def check_cuda_i32(x, name):
+    require(isinstance(x, torch.Tensor), "%s must be a tensor" % name)
+    require(x.is_cuda, "%s: CPU not supported (must be a CUDA tensor)" % name)
+    require(x.is_contiguous(), "%s must be a contiguous tensor" % name)
+    require(x.dtype == torch.int32, "%s must be an int tensor" % name)
+
+
+class Workspace:
+    """Grow-only scratch buffers, one per (device, tag); kept alive so async kernels stay valid."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, device, tag, nbytes):
+        nbytes = int(nbytes)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+
+workspace = Workspace()

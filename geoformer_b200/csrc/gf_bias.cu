@@ -1,0 +1,179 @@
+// The two "distance -> bias" epilogues that consume the geodesic maps.
+//   decoder:   model/geoformer/geoformer_fs.py:680-702 (= geoformer.py:619-641)
+//   mask head: model/geoformer/geoformer_fs.py:263-292 (= geoformer.py:286-313)
+// Both need a per-seed row maximum and the maximum over all seeds before the element-wise part,
+// so each is two kernels: a row-max reduction (with an ordered-int atomicMax for the global
+// maximum) and a fused element-wise pass that writes the reference's output layout directly
+// (no (Q,N,3) boolean-mask temporaries as in the reference).
+#include "gf_common.cuh"
+
+namespace gf {
+
+__device__ __forceinline__ float block_max(float v, float *sm) {
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sm[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, sm[w]);
+  __syncthreads();
+  return r;
+}
+
+__global__ void bias_init_kernel(uint32_t *gmax) { *gmax = 0u; }
+
+// ---- decoder epilogue -------------------------------------------------------------------------------
+// rowmax[q] = max_c geo[q, ctx_idx[c]]      (geoformer_fs.py:685-691)
+__global__ void __launch_bounds__(256)
+    bias_ctx_rowmax_kernel(const float *__restrict__ geo, int ld, const int *__restrict__ ctx_idx, int C,
+                           float *__restrict__ rowmax, uint32_t *__restrict__ gmax) {
+  __shared__ float sm[8];
+  const int q = blockIdx.x;
+  float v = -__int_as_float(0x7f800000);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) v = fmaxf(v, __ldg(geo + (size_t)q * ld + __ldg(ctx_idx + c)));
+  float r = block_max(v, sm);
+  if (threadIdx.x == 0) {
+    rowmax[q] = r;
+    atomicMax(gmax, f2ord(r));  // :692  max over every (batch, query)
+  }
+}
+
+// out[q,c,:] = G >= 0 ? G : m_q + |query_xyz[q] - ctx_xyz[c]|      (:693-702)
+__global__ void __launch_bounds__(256)
+    bias_ctx_write_kernel(const float *__restrict__ geo, int ld, const int *__restrict__ ctx_idx,
+                          const float *__restrict__ query_xyz, const float *__restrict__ ctx_xyz, int Q, int C,
+                          const float *__restrict__ rowmax, const uint32_t *__restrict__ gmax, float *__restrict__ out) {
+  const float M = ord2f(*gmax);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Q * C; e += gridDim.x * blockDim.x) {
+    const int q = e / C, c = e - q * C;
+    float g = __ldg(geo + (size_t)q * ld + __ldg(ctx_idx + c));
+    float m = rowmax[q];
+    if (m < 0.f) m = M;  // :693
+    float o0 = g, o1 = g, o2 = g;
+    if (g < 0.f) {
+      o0 = __fadd_rn(m, fabsf(__fsub_rn(query_xyz[q * 3 + 0], ctx_xyz[c * 3 + 0])));
+      o1 = __fadd_rn(m, fabsf(__fsub_rn(query_xyz[q * 3 + 1], ctx_xyz[c * 3 + 1])));
+      o2 = __fadd_rn(m, fabsf(__fsub_rn(query_xyz[q * 3 + 2], ctx_xyz[c * 3 + 2])));
+    }
+    float *o = out + (size_t)e * 3;
+    o[0] = o0, o[1] = o1, o[2] = o2;
+  }
+}
+
+// ---- mask-head epilogue -----------------------------------------------------------------------------
+// rowmax[q] = max_p geo[q,p]   (:274-275); several CTAs per row, combined with an ordered atomicMax
+__global__ void __launch_bounds__(256)
+    bias_mask_rowmax_kernel(const float *__restrict__ geo, int N, int chunks, uint32_t *__restrict__ rowmax_ord,
+                            uint32_t *__restrict__ gmax) {
+  __shared__ float sm[8];
+  const int q = blockIdx.x / chunks, ch = blockIdx.x - q * chunks;
+  const int per = (N + chunks - 1) / chunks;
+  const int p0 = ch * per, p1 = min(N, p0 + per);
+  float v = -__int_as_float(0x7f800000);
+  for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) v = fmaxf(v, __ldg(geo + (size_t)q * N + p));
+  float r = block_max(v, sm);
+  if (threadIdx.x == 0 && p0 < p1) {
+    atomicMax(rowmax_ord + q, f2ord(r));
+    atomicMax(gmax, f2ord(r));
+  }
+}
+
+// out[q,a,p] = d + (geo[q,p] < 0 ? sqrt(m_q) * sign(d) : 0),  d = seed_xyz[q,a] - coords[p,a]   (:271-289)
+__global__ void __launch_bounds__(256)
+    bias_mask_write_kernel(const float *__restrict__ geo, const float *__restrict__ coords,
+                           const float *__restrict__ seed_xyz, int Q, int N, const uint32_t *__restrict__ rowmax_ord,
+                           const uint32_t *__restrict__ gmax, float *__restrict__ out) {
+  const int q = blockIdx.y;
+  float m = ord2f(rowmax_ord[q]);
+  if (m < 0.f) m = ord2f(*gmax);  // :276
+  const float s = sqrtf(m);       // :277
+  const float sx = seed_xyz[q * 3 + 0], sy = seed_xyz[q * 3 + 1], sz = seed_xyz[q * 3 + 2];
+  float *o = out + (size_t)q * 3 * N;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+    float g = __ldg(geo + (size_t)q * N + p);
+    float dx = __fsub_rn(sx, __ldg(coords + (size_t)p * 3 + 0));
+    float dy = __fsub_rn(sy, __ldg(coords + (size_t)p * 3 + 1));
+    float dz = __fsub_rn(sz, __ldg(coords + (size_t)p * 3 + 2));
+    if (g < 0.f) {
+      float gx = dx > 0.f ? 1.f : (dx < 0.f ? -1.f : dx);  // torch.sign: 0 -> 0, NaN -> NaN
+      float gy = dy > 0.f ? 1.f : (dy < 0.f ? -1.f : dy);
+      float gz = dz > 0.f ? 1.f : (dz < 0.f ? -1.f : dz);
+      dx = __fadd_rn(dx, __fmul_rn(s, gx));
+      dy = __fadd_rn(dy, __fmul_rn(s, gy));
+      dz = __fadd_rn(dz, __fmul_rn(s, gz));
+    }
+    o[p] = dx;
+    o[(size_t)N + p] = dy;
+    o[(size_t)2 * N + p] = dz;
+  }
+}
+
+}  // namespace gf
+
+using namespace gf;
+
+extern "C" size_t gf_bias_workspace_bytes(int B, int Q) {
+  if (B <= 0 || Q <= 0) return 0;
+  return align256(sizeof(float) * (size_t)B * Q) + 256 + 256;
+}
+
+extern "C" int gf_bias_decoder(const float *const *geo_ptrs, const int *geo_ld, const int *ctx_idx,
+                               const float *query_xyz, const float *ctx_xyz, int B, int Q, int C, float *out,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+  GF_CHECK_ARG(B >= 0 && Q >= 0 && C >= 0, "bias_decoder: negative size");
+  if ((long long)B * Q * C == 0) return GF_OK;
+  GF_CHECK_ARG(geo_ptrs && geo_ld && ctx_idx && query_xyz && ctx_xyz && out, "bias_decoder: null pointer");
+  Arena a(workspace, workspace_bytes);
+  float *rowmax = a.take<float>((size_t)B * Q);
+  uint32_t *gmax = a.take<uint32_t>(1);
+  if (!a.ok) {
+    set_error("bias_decoder: workspace too small");
+    return GF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  bias_init_kernel<<<1, 1, 0, st>>>(gmax);
+  GF_LAUNCHED();
+  for (int b = 0; b < B; ++b) {
+    bias_ctx_rowmax_kernel<<<Q, 256, 0, st>>>(geo_ptrs[b], geo_ld[b], ctx_idx + (size_t)b * C, C, rowmax + (size_t)b * Q,
+                                              gmax);
+    GF_LAUNCHED();
+  }
+  for (int b = 0; b < B; ++b) {
+    int grid = (Q * C + 255) / 256;
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    bias_ctx_write_kernel<<<grid, 256, 0, st>>>(geo_ptrs[b], geo_ld[b], ctx_idx + (size_t)b * C,
+                                                query_xyz + (size_t)b * Q * 3, ctx_xyz + (size_t)b * C * 3, Q, C,
+                                                rowmax + (size_t)b * Q, gmax, out + (size_t)b * Q * C * 3);
+    GF_LAUNCHED();
+  }
+  return GF_OK;
+}
+
+extern "C" int gf_bias_mask_head(const float *geo, const float *coords, const float *seed_xyz, int Q, int N,
+                                 float *out, void *workspace, size_t workspace_bytes, void *stream) {
+  GF_CHECK_ARG(Q >= 0 && N >= 0, "bias_mask_head: negative size");
+  if ((long long)Q * N == 0) return GF_OK;
+  GF_CHECK_ARG(geo && coords && seed_xyz && out, "bias_mask_head: null pointer");
+  Arena a(workspace, workspace_bytes);
+  uint32_t *rowmax = a.take<uint32_t>((size_t)Q);
+  uint32_t *gmax = a.take<uint32_t>(1);
+  if (!a.ok) {
+    set_error("bias_mask_head: workspace too small");
+    return GF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  GF_CUDA(cudaMemsetAsync(rowmax, 0, sizeof(uint32_t) * (size_t)Q, st));
+  bias_init_kernel<<<1, 1, 0, st>>>(gmax);
+  GF_LAUNCHED();
+  int chunks = (num_sms() * 8 + Q - 1) / Q;
+  if (chunks < 1) chunks = 1;
+  if (chunks > (N + 1023) / 1024) chunks = (N + 1023) / 1024;
+  bias_mask_rowmax_kernel<<<Q * chunks, 256, 0, st>>>(geo, N, chunks, rowmax, gmax);
+  GF_LAUNCHED();
+  int gx = (N + 255) / 256;
+  int cap = (num_sms() * 16 + Q - 1) / Q;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  bias_mask_write_kernel<<<dim3(gx, Q), 256, 0, st>>>(geo, coords, seed_xyz, Q, N, rowmax, gmax, out);
+  GF_LAUNCHED();
+  return GF_OK;
+}

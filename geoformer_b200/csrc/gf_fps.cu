@@ -1,0 +1,295 @@
+// Furthest point sampling for sm_100a.
+//
+// Reference: lib/pointnet2/_ext_src/src/sampling_gpu.cu:72-232 -- ONE 512-thread block per scene,
+// coordinates and the running min-distance re-read from global memory in each of the m-1 dependent
+// rounds.  GeoFormer calls it with B == 1, so one SM of 148 does everything.
+//
+// Here a scene is owned by a thread-block CLUSTER (up to 16 CTAs x 1024 threads).  Every thread
+// keeps its points AND their running min-distance in registers for the whole kernel (global memory
+// is touched once), so a round is: P fused distance updates per thread -> two REDUX warp
+// reductions -> one shared-memory hop -> the winning CTA-local candidate (key + coordinates) is
+// pushed into every CTA of the cluster through distributed shared memory -> one cluster barrier.
+//
+// Index-exactness.  The reference's result depends on its reduction shape: thread `tid` scans
+// k = tid, tid+bs, ... with a strict '>', then a shared-memory tree keeps the lower slot on ties
+// (sampling_gpu.cu:62-68,111-171).  Among equal maxima the winner is therefore the k with the
+// smallest (bitrev_L(k mod bs), k div bs), bs = 2^L = the reference's block size.  We reproduce it
+// by giving each thread an ascending run of ONE residue class (so its own strict '>' scan keeps the
+// right point) and reducing the 64-bit key (d2 bits, ~rank) with max.
+#include <cooperative_groups.h>
+
+#include "gf_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gf {
+
+struct __align__(16) FpsSlot {
+  uint32_t v, lo;  // key: distance bits, ~rank (0,0 = no eligible point in that CTA)
+  float x, y;
+  float z;
+  float pad[3];
+};
+
+constexpr int FPS_MAX_CLUSTER = 16;
+
+__device__ __forceinline__ uint32_t brev_bits(uint32_t c, int L) { return L ? (__brev(c) >> (32 - L)) : 0u; }
+
+// P > 0 : register-resident variant, thread owns points k = c + bs*(g*P + i), i < P
+// P == 0: streaming variant for scenes that do not fit on chip: thread walks k = c + bs*(g + G*i)
+//         and keeps the running min-distance in `temp` (global, L2 resident)
+template <int T, int P>
+__global__ void __launch_bounds__(T, 1)
+    fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, int L, float *__restrict__ temp_all,
+                       int *__restrict__ idx_all) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned CS = cluster.num_blocks();
+  const unsigned crank = cluster.block_rank();
+  const int scene = blockIdx.x / CS;
+  const float *__restrict__ xyz = xyz_all + (size_t)scene * N * 3;
+  int *__restrict__ idx = idx_all + (size_t)scene * m;
+
+  __shared__ FpsSlot slots[2][FPS_MAX_CLUSTER];
+  __shared__ uint32_t wkey_v[32], wkey_lo[32];
+
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned u = crank * T + tid;  // thread id inside the cluster
+  const unsigned bs = 1u << L;
+  const unsigned c = u & (bs - 1), g = u >> L;
+  const unsigned G = (CS * T) >> L;
+  const uint32_t rank_hi = L ? (brev_bits(c, L) << (32 - L)) : 0u;
+
+  constexpr int PR = P > 0 ? P : 1;
+  float px[PR], py[PR], pz[PR], tmp[PR];
+  uint32_t elig = 0;
+  if (P > 0) {
+#pragma unroll
+    for (int i = 0; i < PR; ++i) {
+      unsigned k = c + bs * (g * PR + i);
+      px[i] = py[i] = pz[i] = 0.f;
+      tmp[i] = 1e10f;  // sampling.cpp:74-76
+      if (k < (unsigned)N) {
+        px[i] = __ldg(xyz + (size_t)k * 3 + 0);
+        py[i] = __ldg(xyz + (size_t)k * 3 + 1);
+        pz[i] = __ldg(xyz + (size_t)k * 3 + 2);
+        float mag = sq3(px[i], py[i], pz[i]);
+        if (!((double)mag <= 1e-3)) elig |= 1u << i;  // sampling_gpu.cu:103-104
+      }
+    }
+  }
+  float *__restrict__ temp = nullptr;
+  if (P == 0) {
+    temp = temp_all + (size_t)scene * N;
+    for (unsigned k = u; k < (unsigned)N; k += CS * T) temp[k] = 1e10f;
+  }
+
+  int old = 0;
+  float cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);
+  if (u == 0) idx[0] = 0;
+  cluster.sync();  // temp initialised (streaming variant), slots not yet in use
+
+  for (int j = 1; j < m; ++j) {
+    float best = -1.f;
+    uint32_t besti = 0;
+    float bx = 0.f, by = 0.f, bz = 0.f;
+    if (P > 0) {
+#pragma unroll
+      for (int i = 0; i < PR; ++i) {
+        if (elig & (1u << i)) {
+          float d = sq3(px[i] - cx, py[i] - cy, pz[i] - cz);
+          float t = fminf(d, tmp[i]);
+          tmp[i] = t;
+          if (t > best) {
+            best = t;
+            besti = i;
+          }
+        }
+      }
+    } else {
+      uint32_t i = 0;
+      for (unsigned k = c + bs * g; k < (unsigned)N; k += bs * G, ++i) {
+        float x = __ldg(xyz + (size_t)k * 3 + 0), y = __ldg(xyz + (size_t)k * 3 + 1), z = __ldg(xyz + (size_t)k * 3 + 2);
+        float mag = sq3(x, y, z);
+        if ((double)mag <= 1e-3) continue;
+        float d = sq3(x - cx, y - cy, z - cz);
+        float t = fminf(d, temp[k]);
+        temp[k] = t;
+        if (t > best) {
+          best = t;
+          besti = g + G * i;
+          bx = x, by = y, bz = z;
+        }
+      }
+    }
+    const bool has = best >= 0.f;
+    const uint32_t vb = has ? __float_as_uint(best) : 0u;
+    const uint32_t rank = rank_hi | (P > 0 ? (g * PR + besti) : besti);
+    const uint32_t lo = has ? ~rank : 0u;
+
+    // warp -> CTA reduction of the 64-bit key with two 32-bit REDUX steps each
+    uint32_t wv = __reduce_max_sync(0xffffffffu, vb);
+    uint32_t wl = __reduce_max_sync(0xffffffffu, vb == wv ? lo : 0u);
+    if (lane == 0) {
+      wkey_v[warp] = wv;
+      wkey_lo[warp] = wl;
+    }
+    __syncthreads();
+    uint32_t tv = lane < T / 32 ? wkey_v[lane] : 0u;
+    uint32_t tl = lane < T / 32 ? wkey_lo[lane] : 0u;
+    const uint32_t cv = __reduce_max_sync(0xffffffffu, tv);
+    const uint32_t cl = __reduce_max_sync(0xffffffffu, tv == cv ? tl : 0u);
+
+    const int buf = j & 1;
+    const bool owner = has && vb == cv && lo == cl;
+    const bool nobody = (cv | cl) == 0u;
+    if (owner || (nobody && tid == 0)) {
+      if (P > 0 && owner) {
+#pragma unroll
+        for (int i = 0; i < PR; ++i)
+          if (besti == (uint32_t)i) bx = px[i], by = py[i], bz = pz[i];
+      }
+      FpsSlot s;
+      s.v = cv, s.lo = cl, s.x = bx, s.y = by, s.z = bz, s.pad[0] = s.pad[1] = s.pad[2] = 0.f;
+      for (unsigned r = 0; r < CS; ++r) {
+        FpsSlot *dst = cluster.map_shared_rank(&slots[buf][crank], r);
+        *dst = s;
+      }
+    }
+    cluster.sync();  // release/acquire: every CTA's candidate is visible in every CTA
+
+    uint32_t gv = 0, gl = 0;
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    for (unsigned r = 0; r < CS; ++r) {
+      FpsSlot s = slots[buf][r];
+      if (s.v > gv || (s.v == gv && s.lo > gl)) gv = s.v, gl = s.lo, nx = s.x, ny = s.y, nz = s.z;
+    }
+    if ((gv | gl) == 0u) {  // no eligible point anywhere: the reference's tree yields index 0
+      old = 0;
+      cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);
+    } else {
+      uint32_t rk = ~gl;
+      old = L ? (int)(((rk & ((1u << (32 - L)) - 1u)) << L) | brev_bits(rk >> (32 - L), L)) : (int)rk;
+      cx = nx, cy = ny, cz = nz;
+    }
+    if (u == 0) idx[j] = old;
+  }
+}
+
+// lib/pointnet2/_ext_src/include/cuda_utils.h:15-21 -- the block size the reference would use
+static int ref_log2_block(int n) {
+  int L = 0;
+  while ((2 << L) <= n && L < 9) ++L;
+  return L;
+}
+
+struct FpsPlan {
+  int T, P, CS;
+};
+
+static FpsPlan plan_fps(int N, int max_cs) {
+  // capacity = CS*T*P (in whole residue-class runs); prefer small clusters, then small P
+  const int cs_opts[5] = {1, 2, 4, 8, 16};
+  const int p_opts[4] = {1, 2, 4, 8};
+  for (int ci = 0; ci < 5; ++ci) {
+    int cs = cs_opts[ci];
+    if (cs > max_cs) break;
+    if ((long long)cs * 1024 * 8 < N) continue;
+    for (int pi = 0; pi < 4; ++pi)
+      if ((long long)cs * 1024 * p_opts[pi] >= N) return {1024, p_opts[pi], cs};
+  }
+  if ((long long)max_cs * 512 * 24 >= N) return {512, 24, max_cs};
+  return {1024, 0, max_cs};
+}
+
+template <int T, int P>
+static int launch_fps(const float *xyz, int B, int N, int m, int L, int CS, float *temp, int *idx, cudaStream_t st) {
+  auto kern = fps_cluster_kernel<T, P>;
+  if (CS > 8) GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)B * CS, 1, 1);
+  cfg.blockDim = dim3(T, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GF_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, L, temp, idx));
+  count_launch();
+  return GF_OK;
+}
+
+static int max_cluster_size() {
+  // 16 (non-portable) when the device can co-schedule a 16-CTA x 1024-thread cluster, else 8
+  static int cached = 0;
+  if (cached) return cached;
+  auto kern = fps_cluster_kernel<1024, 8>;
+  int ok16 = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16, 1, 1);
+    cfg.blockDim = dim3(1024, 1, 1);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n >= 1) ok16 = 1;
+  }
+  (void)cudaGetLastError();
+  cached = ok16 ? 16 : 8;
+  return cached;
+}
+
+}  // namespace gf
+
+using namespace gf;
+
+extern "C" size_t gf_fps_workspace_bytes(int B, int N, int m) {
+  (void)m;
+  if (B <= 0 || N <= 0) return 0;
+  // only the streaming variant needs the (B,N) running-min array; sized for the worst case (8-CTA clusters)
+  if ((long long)8 * 512 * 24 >= N) return 0;
+  return align256(sizeof(float) * (size_t)B * N);
+}
+
+extern "C" int gf_furthest_point_sampling(const float *xyz, int B, int N, int m, int *idx, void *workspace,
+                                          size_t workspace_bytes, void *stream) {
+  GF_CHECK_ARG(B >= 0 && N >= 0 && m >= 0, "furthest_point_sampling: negative size");
+  if (B == 0 || m == 0) return GF_OK;
+  GF_CHECK_ARG(idx, "furthest_point_sampling: null idx");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) {  // nothing to sample from: the zero-initialised output of sampling.cpp:71-73
+    GF_CUDA(cudaMemsetAsync(idx, 0, sizeof(int) * (size_t)B * m, st));
+    return GF_OK;
+  }
+  GF_CHECK_ARG(xyz, "furthest_point_sampling: null xyz");
+  const int L = ref_log2_block(N);
+  FpsPlan p = plan_fps(N, max_cluster_size());
+  float *temp = nullptr;
+  if (p.P == 0) {
+    size_t need = sizeof(float) * (size_t)B * N;
+    if (workspace == nullptr || workspace_bytes < need) {
+      set_error("furthest_point_sampling: N=%d needs a %zu-byte workspace (gf_fps_workspace_bytes)", N, need);
+      return GF_ERR_WORKSPACE;
+    }
+    temp = (float *)workspace;
+  }
+#define GF_FPS_CASE(TT, PP) \
+  if (p.T == TT && p.P == PP) return launch_fps<TT, PP>(xyz, B, N, m, L, p.CS, temp, idx, st)
+  GF_FPS_CASE(1024, 1);
+  GF_FPS_CASE(1024, 2);
+  GF_FPS_CASE(1024, 4);
+  GF_FPS_CASE(1024, 8);
+  GF_FPS_CASE(512, 24);
+  GF_FPS_CASE(1024, 0);
+#undef GF_FPS_CASE
+  set_error("furthest_point_sampling: no kernel variant for N=%d", N);
+  return GF_ERR_INVALID;
+}

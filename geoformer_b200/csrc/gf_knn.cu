@@ -1,0 +1,521 @@
+// Exact L2 k-nearest-neighbour graph for 3-D points on sm_100a.
+//
+// Replaces faiss.GpuIndexFlatL2.search as used by model/geoformer/geodesic_utils.py:11-24
+// (call sites geoformer.py:172-177, geoformer_fs.py:170-175).  Result contract:
+// neighbours ordered by (d2, index), d2 = fmaf(dz,dz, fmaf(dx,dx, dy*dy)) in fp32, k-th missing
+// neighbour = (-1, +inf).
+//
+// Two algorithms, identical results:
+//   algo 0  uniform-grid search.  Points are counting-sorted into cells of edge h (chosen on the
+//           device from the measured cell occupancy, no host round trip); each query walks the
+//           cell shells around its own cell and stops as soon as the k-th best distance is
+//           provably smaller than the distance to every unvisited cell.  Work per query is
+//           O(k) instead of O(N); threads are laid out in cell order so a warp shares its cells.
+//   algo 1  brute-force tiled scan (shared-memory tiles, register-resident sorted top-k).  This
+//           is the formulation named in BASELINE.json; kept as an independent cross-check.
+// 3-D coordinates make this a compare/select problem, not a contraction: no tensor cores.
+#include "gf_knn.cuh"
+
+namespace gf {
+
+constexpr int KNN_MAX_CELLS = 1 << 22;  // dense cell table (2 x 16 MB of int32)
+constexpr int KNN_PASS0_CELLS = 1 << 18;
+constexpr int KNN_SCAN_BLOCKS = 512;
+constexpr int KNN_MAX_DIM = 1024;
+
+// ---- device-side grid description --------------------------------------------------------------
+struct KnnGrid {
+  float ox, oy, oz;  // origin = bbox min
+  float h, inv_h;
+  float slack;  // safety margin of the termination test (absolute length)
+  int dx, dy, dz, ncells;
+  uint32_t mm[6];                  // ordered-uint min xyz, max xyz
+  unsigned long long sum_sq;       // sum over cells of count^2 (occupancy estimate)
+  float tau;                       // target occupancy
+};
+
+__global__ void knn_init_kernel(KnnGrid *g, float tau) {
+  g->mm[0] = g->mm[1] = g->mm[2] = 0xffffffffu;
+  g->mm[3] = g->mm[4] = g->mm[5] = 0u;
+  g->sum_sq = 0ull;
+  g->tau = tau;
+}
+
+__global__ void knn_bbox_kernel(const float *__restrict__ xyz, int N, KnnGrid *g) {
+  uint32_t lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float v = __ldg(xyz + (size_t)i * 3 + a);
+      if (v == v && fabsf(v) <= 3.0e38f) {  // ignore NaN / inf for the box
+        uint32_t o = f2ord(v);
+        lo[a] = min(lo[a], o);
+        hi[a] = max(hi[a], o);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    uint32_t l = __reduce_min_sync(0xffffffffu, lo[a]);
+    uint32_t h = __reduce_max_sync(0xffffffffu, hi[a]);
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&g->mm[a], l);
+      atomicMax(&g->mm[3 + a], h);
+    }
+  }
+}
+
+// pass 0: coarse guess from the bounding-box volume; pass 1: rescale h so that the occupancy seen
+// by a point (sum c^2 / N, measured with the pass-0 grid) becomes the target tau.
+__global__ void knn_plan_kernel(KnnGrid *g, int N, int pass) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float lo[3], ext[3], maxext = 0.f, maxabs = 0.f;
+  for (int a = 0; a < 3; ++a) {
+    bool empty = g->mm[a] == 0xffffffffu && g->mm[3 + a] == 0u;
+    float l = empty ? 0.f : ord2f(g->mm[a]), hgh = empty ? 0.f : ord2f(g->mm[3 + a]);
+    lo[a] = l;
+    ext[a] = hgh - l;
+    maxext = fmaxf(maxext, ext[a]);
+    maxabs = fmaxf(maxabs, fmaxf(fabsf(l), fabsf(hgh)));
+  }
+  if (!(maxext > 0.f)) maxext = 1.f;
+  float h;
+  const int cap = pass == 0 ? KNN_PASS0_CELLS : KNN_MAX_CELLS;
+  if (pass == 0) {
+    float vol = 1.f;
+    for (int a = 0; a < 3; ++a) vol *= fmaxf(ext[a], 1e-3f * maxext);
+    h = cbrtf(vol * g->tau / (float)(N > 0 ? N : 1));
+  } else {
+    float occ = (float)((double)g->sum_sq / (double)(N > 0 ? N : 1));
+    float f = sqrtf(g->tau / fmaxf(occ, 1e-3f));  // surface-like scaling (occupancy ~ h^2)
+    f = fminf(fmaxf(f, 0.125f), 4.f);
+    h = g->h * f;
+    g->sum_sq = 0ull;
+  }
+  h = fmaxf(h, maxext * 1e-6f);
+  h = fmaxf(h, maxext / (float)KNN_MAX_DIM);
+  int d[3];
+  for (int it = 0; it < 64; ++it) {
+    long long cells = 1;
+    for (int a = 0; a < 3; ++a) {
+      d[a] = (int)fminf(floorf(ext[a] / h) + 1.f, (float)KNN_MAX_DIM);
+      if (d[a] < 1) d[a] = 1;
+      cells *= d[a];
+    }
+    if (cells <= cap) break;
+    h *= 1.2599210f;
+  }
+  g->ox = lo[0], g->oy = lo[1], g->oz = lo[2];
+  g->h = h;
+  g->inv_h = 1.f / h;
+  g->dx = d[0], g->dy = d[1], g->dz = d[2];
+  g->ncells = d[0] * d[1] * d[2];
+  // cell membership is decided in fp32: a point may sit one rounding error on the wrong side of
+  // a face.  The slack below is orders of magnitude above that error and costs < 1 % extra rings.
+  g->slack = 1e-3f * h + 4e-6f * maxabs;
+}
+
+__device__ __forceinline__ int cell_coord(float v, float o, float inv_h, int dim) {
+  float f = floorf((v - o) * inv_h);
+  int c = (f >= 0.f) ? (f < (float)dim ? (int)f : dim - 1) : 0;  // NaN -> 0
+  return c;
+}
+__device__ __forceinline__ int cell_of(const KnnGrid &g, float x, float y, float z) {
+  int cx = cell_coord(x, g.ox, g.inv_h, g.dx), cy = cell_coord(y, g.oy, g.inv_h, g.dy),
+      cz = cell_coord(z, g.oz, g.inv_h, g.dz);
+  return (cz * g.dy + cy) * g.dx + cx;
+}
+
+__global__ void knn_zero_cells_kernel(const KnnGrid *__restrict__ g, int *__restrict__ cell_count) {
+  const int n = g->ncells;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cell_count[i] = 0;
+}
+
+__global__ void knn_count_kernel(const float *__restrict__ xyz, int N, const KnnGrid *__restrict__ gp,
+                                 int *__restrict__ cell_count, int *__restrict__ cell_id,
+                                 int *__restrict__ slot_in_cell) {
+  const KnnGrid g = *gp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    float x = __ldg(xyz + (size_t)i * 3), y = __ldg(xyz + (size_t)i * 3 + 1), z = __ldg(xyz + (size_t)i * 3 + 2);
+    int c = cell_of(g, x, y, z);
+    int s = atomicAdd(cell_count + c, 1);
+    if (cell_id) {
+      cell_id[i] = c;
+      slot_in_cell[i] = s;
+    }
+  }
+}
+
+__global__ void knn_occupancy_kernel(KnnGrid *g, const int *__restrict__ cell_count) {
+  const int n = g->ncells;
+  unsigned long long acc = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned long long c = (unsigned long long)cell_count[i];
+    acc += c * c;
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&g->sum_sq, acc);
+}
+
+// ---- exclusive scan of the cell counts (three small kernels, sizes read from the device) -------
+__global__ void __launch_bounds__(256) knn_scan_a(const KnnGrid *__restrict__ g, const int *__restrict__ cnt,
+                                                  int *__restrict__ bsum) {
+  const int n = g->ncells;
+  const int chunk = (n + KNN_SCAN_BLOCKS - 1) / KNN_SCAN_BLOCKS;
+  const int b0 = blockIdx.x * chunk, b1 = min(n, b0 + chunk);
+  int acc = 0;
+  for (int i = b0 + threadIdx.x; i < b1; i += 256) acc += cnt[i];
+  __shared__ int ws[8];
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    bsum[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(KNN_SCAN_BLOCKS) knn_scan_b(int *__restrict__ bsum) {
+  __shared__ int s[KNN_SCAN_BLOCKS];
+  int v = bsum[threadIdx.x];
+  s[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 1; o < KNN_SCAN_BLOCKS; o <<= 1) {
+    int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+    __syncthreads();
+    s[threadIdx.x] += t;
+    __syncthreads();
+  }
+  bsum[threadIdx.x] = s[threadIdx.x] - v;  // exclusive
+}
+
+__global__ void __launch_bounds__(256) knn_scan_c(const KnnGrid *__restrict__ g, const int *__restrict__ cnt,
+                                                  const int *__restrict__ bsum, int *__restrict__ start, int N) {
+  const int n = g->ncells;
+  const int chunk = (n + KNN_SCAN_BLOCKS - 1) / KNN_SCAN_BLOCKS;
+  const int b0 = blockIdx.x * chunk, b1 = min(n, b0 + chunk);
+  __shared__ int ws[8];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = bsum[blockIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x == 0) start[n] = N;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t0 = b0; t0 < b1; t0 += 1024) {
+    int i0 = t0 + threadIdx.x * 4;
+    int c[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[e] = (i0 + e < b1) ? cnt[i0 + e] : 0;
+    int tsum = c[0] + c[1] + c[2] + c[3];
+    int inc = tsum;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += ws[w];
+    int excl = carry + woff + inc - tsum;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (i0 + e < b1) start[i0 + e] = excl;
+      excl += c[e];
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) carry = excl;
+    __syncthreads();
+  }
+}
+
+__global__ void knn_scatter_kernel(const float *__restrict__ xyz, int N, const int *__restrict__ cell_id,
+                                   const int *__restrict__ slot_in_cell, const int *__restrict__ start,
+                                   float4 *__restrict__ sorted, int *__restrict__ order, int *__restrict__ rank) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    int pos = start[cell_id[i]] + slot_in_cell[i];
+    float x = __ldg(xyz + (size_t)i * 3), y = __ldg(xyz + (size_t)i * 3 + 1), z = __ldg(xyz + (size_t)i * 3 + 2);
+    sorted[pos] = make_float4(x, y, z, __int_as_float(i));
+    order[pos] = i;
+    rank[i] = pos;
+  }
+}
+
+// ---- register-resident sorted top-k -------------------------------------------------------------
+// 64-bit keys (d2 bits << 32 | index): lexicographic (d2, index) order, all keys distinct.
+// The list is kept ascending; slots [0, KT-k) are pinned to 0 so that the live part is always the
+// last k entries and list[KT-1] is the current k-th best.
+template <int KT>
+struct TopK {
+  unsigned long long key[KT];
+  __device__ __forceinline__ void init(int k) {
+#pragma unroll
+    for (int i = 0; i < KT; ++i) key[i] = (i < KT - k) ? 0ull : ~0ull;
+  }
+  __device__ __forceinline__ void offer(float d2, int index) {
+    unsigned long long kk = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)index;
+    if (kk < key[KT - 1]) {
+      key[KT - 1] = kk;
+#pragma unroll
+      for (int i = KT - 1; i > 0; --i) {
+        unsigned long long a = key[i - 1], b = key[i];
+        bool sw = b < a;
+        key[i - 1] = sw ? b : a;
+        key[i] = sw ? a : b;
+      }
+    }
+  }
+  __device__ __forceinline__ float kth_d2() const { return __uint_as_float((unsigned)(key[KT - 1] >> 32)); }
+  __device__ __forceinline__ void store(int k, bool do_sqrt, float *__restrict__ dist, long long *__restrict__ i64,
+                                        int *__restrict__ i32) const {
+#pragma unroll
+    for (int i = 0; i < KT; ++i) {
+      int j = i - (KT - k);
+      if (j >= 0) {
+        unsigned long long kk = key[i];
+        bool missing = kk == ~0ull;
+        float d2 = missing ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(kk >> 32));
+        int id = missing ? -1 : (int)(unsigned)(kk & 0xffffffffu);
+        if (dist) dist[j] = do_sqrt ? sqrtf(d2) : d2;
+        if (i64) i64[j] = (long long)id;
+        if (i32) i32[j] = id;
+      }
+    }
+  }
+};
+
+// ---- grid query ---------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(128)
+    knn_grid_query_kernel(const KnnGrid *__restrict__ gp, const float4 *__restrict__ sorted,
+                          const int *__restrict__ start, const float *__restrict__ queries, int nq, int k,
+                          int do_sqrt, float *__restrict__ dist, long long *__restrict__ idx64,
+                          int *__restrict__ idx32) {
+  const KnnGrid g = *gp;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nq) return;
+  float qx, qy, qz;
+  int row;
+  if (queries == nullptr) {
+    float4 me = sorted[s];
+    qx = me.x, qy = me.y, qz = me.z;
+    row = __float_as_int(me.w);
+  } else {
+    qx = __ldg(queries + (size_t)s * 3), qy = __ldg(queries + (size_t)s * 3 + 1), qz = __ldg(queries + (size_t)s * 3 + 2);
+    row = s;
+  }
+  const int cx = cell_coord(qx, g.ox, g.inv_h, g.dx), cy = cell_coord(qy, g.oy, g.inv_h, g.dy),
+            cz = cell_coord(qz, g.oz, g.inv_h, g.dz);
+  TopK<KT> top;
+  top.init(k);
+  const int rmax = max(g.dx, max(g.dy, g.dz));
+  for (int R = 0; R <= rmax; ++R) {
+    const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dz - 1);
+    const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dy - 1);
+    const int xl = cx - R, xr = cx + R;
+    for (int z = z0; z <= z1; ++z) {
+      const bool zface = (z == cz - R) || (z == cz + R);
+      for (int y = y0; y <= y1; ++y) {
+        const bool face = zface || (y == cy - R) || (y == cy + R);
+        const int rowbase = (z * g.dy + y) * g.dx;
+        // on a face of the shell the whole x-run belongs to it; otherwise only its two end cells
+        const int nseg = (face || R == 0) ? 1 : 2;
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+          int xa, xb;
+          if (nseg == 1) {
+            xa = max(xl, 0), xb = min(xr, g.dx - 1);
+          } else {
+            xa = xb = sgi == 0 ? xl : xr;
+            if (xa < 0 || xa >= g.dx) continue;
+          }
+          if (xa > xb) continue;
+          const int p0 = __ldg(start + rowbase + xa), p1 = __ldg(start + rowbase + xb + 1);
+          for (int p = p0; p < p1; ++p) {
+            float4 c = __ldg(sorted + p);
+            float d2 = sq3(c.x - qx, c.y - qy, c.z - qz);
+            top.offer(d2, __float_as_int(c.w));
+          }
+        }
+      }
+    }
+    // distance from the query to the nearest face of the visited block that still has cells
+    // behind it; every unvisited point is at least that far away (minus the fp32 slack)
+    float mfd = __int_as_float(0x7f800000);
+    if (cx - R > 0) mfd = fminf(mfd, qx - (g.ox + (float)(cx - R) * g.h));
+    if (cx + R + 1 < g.dx) mfd = fminf(mfd, (g.ox + (float)(cx + R + 1) * g.h) - qx);
+    if (cy - R > 0) mfd = fminf(mfd, qy - (g.oy + (float)(cy - R) * g.h));
+    if (cy + R + 1 < g.dy) mfd = fminf(mfd, (g.oy + (float)(cy + R + 1) * g.h) - qy);
+    if (cz - R > 0) mfd = fminf(mfd, qz - (g.oz + (float)(cz - R) * g.h));
+    if (cz + R + 1 < g.dz) mfd = fminf(mfd, (g.oz + (float)(cz + R + 1) * g.h) - qz);
+    if (mfd == __int_as_float(0x7f800000)) break;  // the whole grid has been visited
+    float ms = mfd - g.slack;
+    if (ms > 0.f && top.kth_d2() < ms * ms) break;
+  }
+  top.store(k, do_sqrt != 0, dist ? dist + (size_t)row * k : nullptr, idx64 ? idx64 + (size_t)row * k : nullptr,
+            idx32 ? idx32 + (size_t)row * k : nullptr);
+}
+
+// ---- brute force (algo 1) -----------------------------------------------------------------------
+constexpr int BF_TILE = 1024;
+template <int KT>
+__global__ void __launch_bounds__(128)
+    knn_brute_kernel(const float *__restrict__ xyz, int N, const float *__restrict__ queries, int nq, int k,
+                     int do_sqrt, float *__restrict__ dist, long long *__restrict__ idx64, int *__restrict__ idx32) {
+  __shared__ float sx[BF_TILE], sy[BF_TILE], sz[BF_TILE];
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = q < nq;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (live) qx = __ldg(queries + (size_t)q * 3), qy = __ldg(queries + (size_t)q * 3 + 1), qz = __ldg(queries + (size_t)q * 3 + 2);
+  TopK<KT> top;
+  top.init(k);
+  for (int base = 0; base < N; base += BF_TILE) {
+    const int tn = min(BF_TILE, N - base);
+    __syncthreads();
+    for (int t = threadIdx.x; t < tn * 3; t += blockDim.x) {
+      float v = __ldg(xyz + (size_t)base * 3 + t);
+      int pt = t / 3, ax = t - pt * 3;
+      (ax == 0 ? sx : ax == 1 ? sy : sz)[pt] = v;
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll 4
+      for (int t = 0; t < tn; ++t) {
+        float d2 = sq3(sx[t] - qx, sy[t] - qy, sz[t] - qz);
+        top.offer(d2, base + t);
+      }
+    }
+  }
+  if (live)
+    top.store(k, do_sqrt != 0, dist ? dist + (size_t)q * k : nullptr, idx64 ? idx64 + (size_t)q * k : nullptr,
+              idx32 ? idx32 + (size_t)q * k : nullptr);
+}
+
+// ---- host orchestration -------------------------------------------------------------------------
+size_t knn_grid_workspace_bytes(int N) {
+  size_t b = 0;
+  b += align256(sizeof(KnnGrid));
+  b += align256(sizeof(int) * (size_t)(KNN_MAX_CELLS + 1)) * 2;  // cell_count, cell_start
+  b += align256(sizeof(int) * KNN_SCAN_BLOCKS);
+  b += align256(sizeof(int) * (size_t)N) * 4;  // cell_id, slot_in_cell, order, rank
+  b += align256(sizeof(float4) * (size_t)N);
+  return b + 1024;
+}
+
+template <int KT>
+static void launch_grid_query(const KnnGrid *g, const float4 *sorted, const int *start, const float *queries, int nq,
+                              int k, int do_sqrt, float *dist, long long *i64, int *i32, cudaStream_t st) {
+  knn_grid_query_kernel<KT><<<(nq + 127) / 128, 128, 0, st>>>(g, sorted, start, queries, nq, k, do_sqrt, dist, i64, i32);
+}
+template <int KT>
+static void launch_brute(const float *xyz, int N, const float *queries, int nq, int k, int do_sqrt, float *dist,
+                         long long *i64, int *i32, cudaStream_t st) {
+  knn_brute_kernel<KT><<<(nq + 127) / 128, 128, 0, st>>>(xyz, N, queries, nq, k, do_sqrt, dist, i64, i32);
+}
+
+int knn_grid_build(const float *xyz, int N, int k, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                   KnnGridBuffers *out) {
+  Arena a(workspace, workspace_bytes);
+  KnnGrid *g = a.take<KnnGrid>(1);
+  int *cell_count = a.take<int>(KNN_MAX_CELLS + 1);
+  int *cell_start = a.take<int>(KNN_MAX_CELLS + 1);
+  int *bsum = a.take<int>(KNN_SCAN_BLOCKS);
+  int *cell_id = a.take<int>(N);
+  int *slot = a.take<int>(N);
+  int *order = a.take<int>(N);
+  int *rank = a.take<int>(N);
+  float4 *sorted = a.take<float4>(N);
+  if (!a.ok) {
+    set_error("knn: workspace too small (%zu bytes given, %zu needed)", workspace_bytes, knn_grid_workspace_bytes(N));
+    return GF_ERR_WORKSPACE;
+  }
+  const int nb = num_sms() * 8;
+  const float tau = fmaxf(2.f, 0.45f * (float)k);
+  knn_init_kernel<<<1, 1, 0, st>>>(g, tau);
+  GF_LAUNCHED();
+  knn_bbox_kernel<<<min(nb, (N + 255) / 256), 256, 0, st>>>(xyz, N, g);
+  GF_LAUNCHED();
+  // pass 0: coarse grid, only to measure the occupancy
+  knn_plan_kernel<<<1, 1, 0, st>>>(g, N, 0);
+  GF_LAUNCHED();
+  knn_zero_cells_kernel<<<nb, 256, 0, st>>>(g, cell_count);
+  GF_LAUNCHED();
+  knn_count_kernel<<<min(nb, (N + 255) / 256), 256, 0, st>>>(xyz, N, g, cell_count, nullptr, nullptr);
+  GF_LAUNCHED();
+  knn_occupancy_kernel<<<nb, 256, 0, st>>>(g, cell_count);
+  GF_LAUNCHED();
+  // pass 1: final grid
+  knn_plan_kernel<<<1, 1, 0, st>>>(g, N, 1);
+  GF_LAUNCHED();
+  knn_zero_cells_kernel<<<nb, 256, 0, st>>>(g, cell_count);
+  GF_LAUNCHED();
+  knn_count_kernel<<<min(nb, (N + 255) / 256), 256, 0, st>>>(xyz, N, g, cell_count, cell_id, slot);
+  GF_LAUNCHED();
+  knn_scan_a<<<KNN_SCAN_BLOCKS, 256, 0, st>>>(g, cell_count, bsum);
+  GF_LAUNCHED();
+  knn_scan_b<<<1, KNN_SCAN_BLOCKS, 0, st>>>(bsum);
+  GF_LAUNCHED();
+  knn_scan_c<<<KNN_SCAN_BLOCKS, 256, 0, st>>>(g, cell_count, bsum, cell_start, N);
+  GF_LAUNCHED();
+  knn_scatter_kernel<<<min(nb, (N + 255) / 256), 256, 0, st>>>(xyz, N, cell_id, slot, cell_start, sorted, order, rank);
+  GF_LAUNCHED();
+  out->grid = g;
+  out->cell_start = cell_start;
+  out->sorted = sorted;
+  out->order = order;
+  out->rank = rank;
+  return GF_OK;
+}
+
+int knn_grid_query(const KnnGridBuffers &b, const float *queries, int nq, int k, int do_sqrt, float *dist,
+                   long long *idx64, int *idx32, cudaStream_t st) {
+  const KnnGrid *g = (const KnnGrid *)b.grid;
+  if (k <= 8)
+    launch_grid_query<8>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, st);
+  else if (k <= 16)
+    launch_grid_query<16>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, st);
+  else if (k <= 32)
+    launch_grid_query<32>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, st);
+  else
+    launch_grid_query<64>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, st);
+  GF_LAUNCHED();
+  return GF_OK;
+}
+
+}  // namespace gf
+
+using namespace gf;
+
+extern "C" size_t gf_knn_workspace_bytes(int N, int nq, int k, int algo) {
+  (void)nq;
+  (void)k;
+  if (algo == 1 || N <= 0) return 0;
+  return knn_grid_workspace_bytes(N);
+}
+
+extern "C" int gf_knn(const float *xyz, int N, const float *queries, int nq, int k, int sqrt_out, float *dist,
+                      int64_t *idx64, int32_t *idx32, int algo, void *workspace, size_t workspace_bytes,
+                      void *stream) {
+  GF_CHECK_ARG(N >= 0 && nq >= 0, "knn: negative size");
+  GF_CHECK_ARG(k >= 1 && k <= KNN_MAX_K, "knn: k=%d outside [1,%d]", k, KNN_MAX_K);
+  GF_CHECK_ARG(algo == 0 || algo == 1, "knn: unknown algo %d", algo);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (queries == nullptr) nq = N;
+  if (nq == 0) return GF_OK;
+  GF_CHECK_ARG(xyz || N == 0, "knn: null xyz");
+  if (algo == 1 || N == 0) {
+    const float *q = queries ? queries : xyz;
+    if (k <= 8)
+      launch_brute<8>(xyz, N, q, nq, k, sqrt_out, dist, (long long *)idx64, idx32, st);
+    else if (k <= 16)
+      launch_brute<16>(xyz, N, q, nq, k, sqrt_out, dist, (long long *)idx64, idx32, st);
+    else if (k <= 32)
+      launch_brute<32>(xyz, N, q, nq, k, sqrt_out, dist, (long long *)idx64, idx32, st);
+    else
+      launch_brute<64>(xyz, N, q, nq, k, sqrt_out, dist, (long long *)idx64, idx32, st);
+    GF_LAUNCHED();
+    return GF_OK;
+  }
+  KnnGridBuffers b;
+  int rc = knn_grid_build(xyz, N, k, workspace, workspace_bytes, st, &b);
+  if (rc) return rc;
+  return knn_grid_query(b, queries, nq, k, sqrt_out, dist, (long long *)idx64, idx32, st);
+}

@@ -1,0 +1,91 @@
+"""The fused hot path: FPS seeds -> kNN graph -> geodesic maps of one scene.
+
+geodesic_guidance      : device tensors in, device tensors out (asynchronous on the current stream)
+HostGuidance           : host buffers in, host buffers out through gf_guidance_host (the call the
+                         benchmark's `e2e` number times: H2D of the points and D2H of the maps
+                         are inside the call)
+"""
+import ctypes
+
+import torch
+
+from . import _capi as C
+
+
+def geodesic_guidance(xyz, n_queries, neighbor, radius, max_step, return_graph=False, return_stats=False):
+    """xyz (N,3) f32 CUDA -> (seeds (Q,) i32, geo (Q,N) f32 [, D (N,k) f32, I (N,k) i32][, stats (2,) i64])."""
+    C.check_cuda_f32(xyz, "xyz")
+    C.require(xyz.dim() == 2 and xyz.size(1) == 3, "xyz must be (N, 3)")
+    N, Q, k = xyz.size(0), int(n_queries), int(neighbor)
+    dev = xyz.device
+    seeds = torch.empty((Q,), dtype=torch.int32, device=dev)
+    geo = torch.empty((Q, N), dtype=torch.float32, device=dev)
+    D = torch.empty((N, k), dtype=torch.float32, device=dev) if return_graph else None
+    I = torch.empty((N, k), dtype=torch.int32, device=dev) if return_graph else None
+    stats = torch.zeros(2, dtype=torch.int64, device=dev) if return_stats else None
+    L = C.lib()
+    with torch.cuda.device(dev):
+        nbytes = L.gf_guidance_workspace_bytes(N, Q, k)
+        ws = C.workspace.get(dev, "guidance", nbytes)
+        C.check(L.gf_guidance(C.ptr(xyz), N, Q, k, ctypes.c_float(float(radius)), int(max_step), C.ptr(seeds),
+                              C.ptr(geo), C.ptr(D), C.ptr(I), C.ptr(stats), C.ptr(ws), nbytes, C.stream_of(dev)),
+                "guidance")
+    out = [seeds, geo]
+    if return_graph:
+        out += [D, I]
+    if return_stats:
+        out.append(stats)
+    return tuple(out)
+
+
+class GuidanceRunner:
+    """Pre-allocated device-resident runner (no allocation per call): run(xyz) -> (seeds, geo) views
+    of its own buffers, valid until the next run().  Used by bench.py for the kernel-only number."""
+
+    def __init__(self, N, n_queries, neighbor, radius, max_step, device="cuda"):
+        self.N, self.Q, self.k = int(N), int(n_queries), int(neighbor)
+        self.radius, self.max_step = float(radius), int(max_step)
+        self.device = torch.device(device)
+        self.seeds = torch.empty((self.Q,), dtype=torch.int32, device=self.device)
+        self.geo = torch.empty((self.Q, self.N), dtype=torch.float32, device=self.device)
+        self.stats = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._L = C.lib()
+        self._nbytes = self._L.gf_guidance_workspace_bytes(self.N, self.Q, self.k)
+        self._ws = torch.empty(self._nbytes, dtype=torch.uint8, device=self.device)
+
+    def run(self, xyz, stream=None):
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        C.check(self._L.gf_guidance(C.ptr(xyz), self.N, self.Q, self.k, ctypes.c_float(self.radius), self.max_step,
+                                    C.ptr(self.seeds), C.ptr(self.geo), None, None, C.ptr(self.stats),
+                                    C.ptr(self._ws), self._nbytes, ctypes.c_void_p(st.cuda_stream)), "guidance")
+        return self.seeds, self.geo
+
+
+class HostGuidance:
+    """Host-buffer entry point.  run(xyz_host) copies the points to the device, runs the hot path and
+    copies seeds and maps back, all inside gf_guidance_host (blocking; releases the GIL, so several
+    HostGuidance objects driven from different Python threads overlap copies with compute)."""
+
+    def __init__(self, N, n_queries, neighbor, radius, max_step, device="cuda", pinned=True):
+        self.N, self.Q, self.k = int(N), int(n_queries), int(neighbor)
+        self.radius, self.max_step = float(radius), int(max_step)
+        self.device = torch.device(device)
+        self._L = C.lib()
+        self._nbytes = self._L.gf_guidance_host_workspace_bytes(self.N, self.Q, self.k)
+        self._ws = torch.empty(self._nbytes, dtype=torch.uint8, device=self.device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.seeds_host = torch.empty((self.Q,), dtype=torch.int32, pin_memory=pinned)
+        self.geo_host = torch.empty((self.Q, self.N), dtype=torch.float32, pin_memory=pinned)
+        self.h2d_bytes = self.N * 3 * 4
+        self.d2h_bytes = self.Q * 4 + self.Q * self.N * 4
+
+    def run(self, xyz_host):
+        C.require(not xyz_host.is_cuda and xyz_host.dtype == torch.float32 and xyz_host.is_contiguous(),
+                  "xyz_host must be a contiguous float32 CPU tensor")
+        C.require(tuple(xyz_host.shape) == (self.N, 3), "xyz_host must be (N, 3)")
+        with torch.cuda.device(self.device):
+            C.check(self._L.gf_guidance_host(C.ptr(xyz_host), self.N, self.Q, self.k, ctypes.c_float(self.radius),
+                                             self.max_step, C.ptr(self.seeds_host), C.ptr(self.geo_host),
+                                             C.ptr(self._ws), self._nbytes,
+                                             ctypes.c_void_p(self.stream.cuda_stream)), "guidance_host")
+        return self.seeds_host, self.geo_host
