@@ -423,8 +423,13 @@ def test_group_points_pipeline_and_autograd(oracle_lib, dev):
     assert np.array_equal(new_xyz.cpu().numpy(), r_new)
     r_idx = oracle_lib.ball_query(np.ascontiguousarray(r_new), x.numpy(), 0.2, 64)
     r_gx = oracle_lib.group_points(x.transpose(1, 2).contiguous().numpy(), r_idx)
-    r_gx = (torch.from_numpy(r_gx) - torch.from_numpy(np.ascontiguousarray(r_new)).transpose(1, 2).unsqueeze(-1)) / 0.2
-    assert torch.equal(gx.cpu(), r_gx)
+    r_gx_raw = torch.from_numpy(r_gx) - torch.from_numpy(np.ascontiguousarray(r_new)).transpose(1, 2).unsqueeze(-1)
+    r_gx = r_gx_raw / 0.2
+    # torch's CUDA `/= scalar` multiplies by the reciprocal (not our kernel): allow its 1-ulp difference
+    torch.testing.assert_close(gx.cpu(), r_gx, rtol=1e-6, atol=1e-7)
+    grouper_raw = pu.QueryAndGroup(0.2, 64, use_xyz=True, ret_grouped_xyz=True, normalize_xyz=False)
+    _, _, gx_raw, _ = pu.group_points(x.to(dev), fd, grouper_raw, 128)
+    assert torch.equal(gx_raw.cpu(), r_gx_raw)
     assert gf.shape == (1, 19, 128, 64)
     assert np.array_equal(gf[:, 3:].detach().cpu().numpy(), oracle_lib.group_points(feats.numpy(), r_idx))
     gf.sum().backward()
