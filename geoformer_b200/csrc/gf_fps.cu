@@ -157,11 +157,17 @@ __global__ void __launch_bounds__(T, 1)
     }
     cluster.sync();  // release/acquire: every CTA's candidate is visible in every CTA
 
-    uint32_t gv = 0, gl = 0;
+    // lane r looks at CTA r's candidate; two REDUX steps pick the cluster-wide winner
+    uint32_t sv = 0, sl = 0;
+    if (lane < CS) sv = slots[buf][lane].v, sl = slots[buf][lane].lo;
+    const uint32_t gv = __reduce_max_sync(0xffffffffu, sv);
+    const uint32_t gl = __reduce_max_sync(0xffffffffu, sv == gv ? sl : 0u);
+    const unsigned wl_mask = __ballot_sync(0xffffffffu, lane < CS && sv == gv && sl == gl);
+    const int wr = __ffs(wl_mask) - 1;  // (gv,gl) != 0 -> exactly one lane; == 0 -> unused
     float nx = 0.f, ny = 0.f, nz = 0.f;
-    for (unsigned r = 0; r < CS; ++r) {
-      FpsSlot s = slots[buf][r];
-      if (s.v > gv || (s.v == gv && s.lo > gl)) gv = s.v, gl = s.lo, nx = s.x, ny = s.y, nz = s.z;
+    if (wr >= 0) {
+      const FpsSlot &ws = slots[buf][wr];
+      nx = ws.x, ny = ws.y, nz = ws.z;
     }
     if ((gv | gl) == 0u) {  // no eligible point anywhere: the reference's tree yields index 0
       old = 0;

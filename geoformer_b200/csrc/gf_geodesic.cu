@@ -8,367 +8,357 @@
 // 131-136 keep the first occurrence of each (point, query) pair; the candidate list is built from
 // the lexicographically sorted winner list of the previous level, :131-135, :154).
 //
-// Formulation here ("pull, bit-parallel over seeds"):
-//   * the kNN graph (radius-filtered, column 0 dropped) is transposed ONCE per scene into a
-//     reverse CSR whose rows are sorted by (parent index, slot) -- the reference's tie order;
-//   * visited / frontier sets are bit matrices [point][seed word]: one 32-bit word serves 32
-//     seeds, a whole row of 256 seeds is one 32-byte sector;
-//   * one persistent cooperative kernel runs all levels (grid barrier between levels, no host
-//     synchronisation -- the reference syncs the host >= 3 times per level).  In a level every
-//     (target, word) thread walks the target's in-edges in tie order and takes, for each seed bit
-//     that is still unvisited, the FIRST parent whose frontier bit is set: no atomics, no
-//     sort/unique, deterministic, and exactly the reference's winner.
-//   * distances live directly in the (Q,N) output; one fp32 add per reached pair, as the reference.
-// Points are optionally renumbered in the cell order of the kNN grid (order/rank) so that the
-// frontier rows a warp touches are neighbours in memory; tie-breaking still uses ORIGINAL indices.
-#include <cooperative_groups.h>
+// Formulation: the Q seeds are independent BFS runs over the same graph, so ONE CTA owns ONE seed
+// from its first level to its last (persistent CTAs pull seeds from a counter).  All level
+// synchronisation is a __syncthreads() -- no grid barrier, no host round trip (the reference
+// synchronises the host >= 3 times per level) -- and the state of a run lives on chip:
+//   * visited set: a bitmap in shared memory (N bits);
+//   * frontier: a compacted queue of (point, distance) pairs in shared memory (global overflow);
+//   * the seed's own output row geo[q][:] doubles as the claim array.  An unvisited entry holds
+//     -1.0f = 0xBF800000.  A candidate (parent p, slot j) -> t claims t with
+//         atomicMin(bits(geo[q][t]), 0x80000000 | (p << SB | j))
+//     which is smaller than "unvisited", larger than any finished distance (a non-negative float,
+//     < 0x80000000), and ordered exactly like the reference's tie rule (parent index, then slot).
+//     After a CTA barrier the candidate whose key is still in place is the winner: it overwrites
+//     the key with the distance D[p][j] + dist(p) (one fp32 add, as the reference), sets the
+//     visited bit and appends (t, distance) to the next frontier.
+// Work is proportional to the edges actually expanded (R*K), the kNN rows are streamed straight
+// from the forward graph (no transpose / sort / unique), and nothing is allocated per level.
+#include <stdlib.h>
 
 #include "gf_geodesic.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace gf {
 
-// ---- generic exclusive scan over n ints (n known on the host) ------------------------------------
-constexpr int SCAN_BLOCKS = 512;
+constexpr int GEO_THREADS = 512;
+constexpr int GEO_QCAP = 2048;                   // frontier entries kept in shared memory (per buffer)
+constexpr int GEO_SCAP = 4096;                   // claimants of one level kept in shared memory
+constexpr int GEO_UNROLL = 4;
+constexpr uint32_t GEO_UNVISITED = 0xBF800000u;  // bits of -1.0f
+constexpr uint32_t GEO_KEYBIT = 0x80000000u;
+constexpr uint32_t GEO_KEYMAX = 0x3F800000u;  // keys must stay below "unvisited"
 
-__global__ void __launch_bounds__(256) scan_a_kernel(const int *__restrict__ in, int n, int *__restrict__ bsum) {
-  const int chunk = (n + SCAN_BLOCKS - 1) / SCAN_BLOCKS;
-  const int b0 = blockIdx.x * chunk, b1 = min(n, b0 + chunk);
-  int acc = 0;
-  for (int i = b0 + threadIdx.x; i < b1; i += 256) acc += in[i];
-  __shared__ int ws[8];
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int w = 0; w < 8; ++w) t += ws[w];
-    bsum[blockIdx.x] = t;
-  }
+struct GeoArgs {
+  const float *D;  // (N,k) sqrt'ed kNN distances
+  const void *I;   // (N,k) int32 / int64 neighbour indices
+  int N, k, Q, max_step;
+  float radius;
+  const int *seeds;
+  float *geo;                 // (Q,N)
+  int2 *overflow;             // per CTA: N+2 frontier entries beyond GEO_QCAP (two stacks, one per end)
+  unsigned *seed_counter;     // work distribution
+  unsigned long long *stats;  // [0] reached pairs, [1] deepest level (atomicMax)
+  int bitmap_words;           // shared-memory visited bitmap size (0 = test the output row instead)
+  int slot_bits;              // key layout / candidate indexing (slots padded to 2^slot_bits)
+};
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
-__global__ void __launch_bounds__(SCAN_BLOCKS) scan_b_kernel(int *__restrict__ bsum) {
-  __shared__ int s[SCAN_BLOCKS];
-  int v = bsum[threadIdx.x];
-  s[threadIdx.x] = v;
-  __syncthreads();
-  for (int o = 1; o < SCAN_BLOCKS; o <<= 1) {
-    int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
-    __syncthreads();
-    s[threadIdx.x] += t;
-    __syncthreads();
-  }
-  bsum[threadIdx.x] = s[threadIdx.x] - v;
+// Frontier entry i: the first GEO_QCAP live in shared memory, the rest in the CTA's global overflow
+// area.  Consecutive levels hold disjoint point sets (F_L + F_{L+1} <= N + 1), so ONE buffer of N + 2
+// entries serves both: odd levels grow up from index 0, even levels grow down from the top.
+__device__ __forceinline__ size_t ovf_index(int i, int level_parity, int N) {
+  const size_t j = (size_t)(i - GEO_QCAP);
+  return level_parity ? j : (size_t)N + 1 - j;
+}
+__device__ __forceinline__ int2 frontier_get(const int2 *sq, const int2 *ovf, int i, int level_parity, int N) {
+  return i < GEO_QCAP ? sq[i] : ovf[ovf_index(i, level_parity, N)];
 }
 
-// out[i] = sum(in[0..i)), out[n] = total
-__global__ void __launch_bounds__(256) scan_c_kernel(const int *__restrict__ in, int n, const int *__restrict__ bsum,
-                                                     int *__restrict__ out) {
-  const int chunk = (n + SCAN_BLOCKS - 1) / SCAN_BLOCKS;
-  const int b0 = blockIdx.x * chunk, b1 = min(n, b0 + chunk);
-  __shared__ int ws[8];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = bsum[blockIdx.x];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int t0 = b0; t0 < b1; t0 += 1024) {
-    int i0 = t0 + threadIdx.x * 4;
-    int c[4];
+// warp-aggregated append: one shared-memory atomic per warp instead of one per lane
+__device__ __forceinline__ int warp_append_pos(bool want, int *counter) {
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  int base = 0;
+  const unsigned lane = threadIdx.x & 31;
+  if (m && lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, m ? __ffs(m) - 1 : 0);
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
+template <bool IS64>
+__global__ void __launch_bounds__(GEO_THREADS) geo_seed_bfs_kernel(const GeoArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int2 *q0 = reinterpret_cast<int2 *>(smem_raw);
+  int2 *q1 = q0 + GEO_QCAP;
+  int *sv_t = reinterpret_cast<int *>(q1 + GEO_QCAP);  // survivors of pass A: target, key, distance bits
+  uint32_t *sv_key = reinterpret_cast<uint32_t *>(sv_t + GEO_SCAP);
+  int *sv_d = reinterpret_cast<int *>(sv_key + GEO_SCAP);
+  uint32_t *vis = reinterpret_cast<uint32_t *>(sv_d + GEO_SCAP);
+  __shared__ int s_next_n, s_seed_q, s_surv_n;
+  __shared__ unsigned long long s_reached;
+
+  const int N = a.N, k = a.k, K = a.k - 1;
+  const int KP = 1 << a.slot_bits;
+  const float radius = a.radius;
+  const int tid = threadIdx.x;
+  int2 *ovf = a.overflow + (size_t)blockIdx.x * ((size_t)N + 2);
+  unsigned long long reached_total = 0;  // thread 0 only
+  int deepest = 0;
+
+  for (;;) {
+    if (tid == 0) s_seed_q = (int)atomicAdd(a.seed_counter, 1u);
+    __syncthreads();
+    const int q = s_seed_q;
+    if (q >= a.Q) break;
+    float *row = a.geo + (size_t)q * N;
+    uint32_t *rowu = reinterpret_cast<uint32_t *>(row);
+    // ---- init: row = -1 (geodesic_utils.py:113), visited = {} (:114) -------------------------------
+    {
+      const size_t head = ((16 - ((uintptr_t)row & 15)) & 15) / 4;
+      const size_t h = head < (size_t)N ? head : (size_t)N;
+      const size_t nvec = ((size_t)N - h) / 4;
+      float4 *r4 = reinterpret_cast<float4 *>(row + h);
+      const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
+      for (size_t i = tid; i < nvec; i += GEO_THREADS) r4[i] = m1;
+      if ((size_t)tid < h) row[tid] = -1.f;
+      const size_t tail0 = h + nvec * 4;
+      if ((size_t)tid < (size_t)N - tail0) row[tail0 + tid] = -1.f;
+      for (int i = tid; i < a.bitmap_words; i += GEO_THREADS) vis[i] = 0u;
+    }
+    const int s = a.seeds[q];
+    const bool seed_ok = s >= 0 && s < N;  // the reference would raise an index error; the row stays -1
+    if (tid == 0) {
+      s_next_n = 0;
+      s_surv_n = 0;
+      s_reached = 0ull;
+      if (seed_ok) q0[0] = make_int2(s, __float_as_int(0.f));  // :118, distance of the seed
+    }
+    __syncthreads();
+    int F = seed_ok ? 1 : 0;
+    int2 *fq = q0, *nq = q1;
+    // NOTE the seed is NOT marked visited before level 1: the reference's first expansion has no
+    // visited filter (:123), so a seed that appears in its own neighbour row is re-won at level 1.
+    int level = 0;
+    while (F > 0 && level < a.max_step) {
+      ++level;
+      const int par = (level - 1) & 1;
+      const long long ncand = (long long)F << a.slot_bits;
+      // ---- pass A: every valid candidate claims its target; claimants are remembered -----------------
+      // batches of GEO_UNROLL candidates per thread: all neighbour loads of a batch are in flight
+      // together (the propagation is latency bound: short dependent chains, little work per level)
+      // (loop bounds are warp-uniform: the appends below use full-warp ballots)
+      for (long long wbase = tid & ~31; wbase < ncand; wbase += (long long)GEO_THREADS * GEO_UNROLL) {
+        const long long base = wbase + (tid & 31);
+        int2 pe[GEO_UNROLL];
+        int slot[GEO_UNROLL];
+        long long t[GEO_UNROLL];
+        float w[GEO_UNROLL];
+        bool ok[GEO_UNROLL];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) c[e] = (i0 + e < b1) ? in[i0 + e] : 0;
-    int tsum = c[0] + c[1] + c[2] + c[3];
-    int inc = tsum;
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) ws[warp] = inc;
-    __syncthreads();
-    int woff = 0;
-    for (int w = 0; w < warp; ++w) woff += ws[w];
-    int excl = carry + woff + inc - tsum;
+        for (int u = 0; u < GEO_UNROLL; ++u) {
+          const long long c = base + (long long)u * GEO_THREADS;
+          slot[u] = (int)(c & (KP - 1));
+          ok[u] = c < ncand && slot[u] < K;
+          pe[u] = ok[u] ? frontier_get(fq, ovf, (int)(c >> a.slot_bits), par, N) : make_int2(0, 0);
+        }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (i0 + e < b1) out[i0 + e] = excl;
-      excl += c[e];
-    }
-    __syncthreads();
-    if (threadIdx.x == 255) carry = excl;
-    __syncthreads();
-  }
-  if (b1 == n && b0 < n && threadIdx.x == 0) out[n] = carry;
-  if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0;
-}
-
-static int exclusive_scan(const int *in, int n, int *out, int *bsum, cudaStream_t st) {
-  scan_a_kernel<<<SCAN_BLOCKS, 256, 0, st>>>(in, n, bsum);
-  GF_LAUNCHED();
-  scan_b_kernel<<<1, SCAN_BLOCKS, 0, st>>>(bsum);
-  GF_LAUNCHED();
-  scan_c_kernel<<<SCAN_BLOCKS, 256, 0, st>>>(in, n, bsum, out);
-  GF_LAUNCHED();
-  return GF_OK;
-}
-
-// ---- reverse CSR construction ---------------------------------------------------------------------
-__device__ __forceinline__ long long load_idx(const void *idx, int is64, size_t at) {
-  return is64 ? ((const long long *)idx)[at] : (long long)((const int *)idx)[at];
-}
-
-// one thread per forward edge (p, slot j of the K = k-1 usable columns); valid iff D <= radius and
-// 0 <= I < N (geodesic_utils.py:123,151)
-__global__ void geo_count_edges_kernel(const float *__restrict__ D, const void *__restrict__ I, int is64, int N, int k,
-                                       float radius, const int *__restrict__ rank, int *__restrict__ rev_count) {
-  const int K = k - 1;
-  const long long total = (long long)N * K;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    int p = (int)(e / K), j = (int)(e - (long long)p * K);
-    size_t at = (size_t)p * k + 1 + j;
-    long long t = load_idx(I, is64, at);
-    if (__ldg(D + at) <= radius && t >= 0 && t < N) atomicAdd(rev_count + (rank ? __ldg(rank + t) : (int)t), 1);
-  }
-}
-
-__global__ void geo_fill_edges_kernel(const float *__restrict__ D, const void *__restrict__ I, int is64, int N, int k,
-                                      float radius, const int *__restrict__ rank, const int *__restrict__ rev_start,
-                                      int *__restrict__ cursor, unsigned long long *__restrict__ rev_key) {
-  const int K = k - 1;
-  const long long total = (long long)N * K;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    int p = (int)(e / K), j = (int)(e - (long long)p * K);
-    size_t at = (size_t)p * k + 1 + j;
-    long long t = load_idx(I, is64, at);
-    if (__ldg(D + at) <= radius && t >= 0 && t < N) {
-      int ti = rank ? __ldg(rank + t) : (int)t;
-      int s = atomicAdd(cursor + ti, 1);
-      rev_key[(size_t)__ldg(rev_start + ti) + s] = ((unsigned long long)(unsigned)p << 8) | (unsigned)j;
-    }
-  }
-}
-
-// one thread per target row: order the in-edges by (original parent index, slot) -- the reference's
-// tie order -- then rewrite each 64-bit key in place as {internal parent id, edge length bits}
-__global__ void geo_sort_rows_kernel(const float *__restrict__ D, int N, int k, const int *__restrict__ rank,
-                                     const int *__restrict__ rev_start, unsigned long long *__restrict__ rev) {
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N; t += gridDim.x * blockDim.x) {
-    const int e0 = rev_start[t], e1 = rev_start[t + 1];
-    for (int a = e0 + 1; a < e1; ++a) {
-      unsigned long long key = rev[a];
-      int b = a - 1;
-      while (b >= e0 && rev[b] > key) {
-        rev[b + 1] = rev[b];
-        --b;
-      }
-      rev[b + 1] = key;
-    }
-    for (int a = e0; a < e1; ++a) {
-      unsigned long long key = rev[a];
-      unsigned p = (unsigned)(key >> 8), j = (unsigned)(key & 255u);
-      unsigned pi = rank ? (unsigned)__ldg(rank + p) : p;
-      unsigned wb = __float_as_uint(__ldg(D + (size_t)p * k + 1 + j));
-      rev[a] = ((unsigned long long)wb << 32) | pi;  // as uint2: .x = parent, .y = length bits
-    }
-  }
-}
-
-// ---- state initialisation ---------------------------------------------------------------------------
-__global__ void geo_fill_kernel(float *__restrict__ geo, size_t n, float v) {
-  // vectorised bulk + scalar head/tail (geo is only guaranteed 4-byte aligned)
-  size_t head = ((16 - ((uintptr_t)geo & 15)) & 15) / 4;
-  if (head > n) head = n;
-  size_t nvec = (n - head) / 4;
-  float4 *g4 = (float4 *)(geo + head);
-  const float4 vv = make_float4(v, v, v, v);
-  size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = tid; i < nvec; i += stride) g4[i] = vv;
-  if (tid < head) geo[tid] = v;
-  size_t tail0 = head + nvec * 4;
-  if (tid < n - tail0) geo[tail0 + tid] = v;
-}
-
-__global__ void geo_seed_kernel(const int *__restrict__ seeds, int Q, int N, int W, const int *__restrict__ rank,
-                                float *__restrict__ geo, uint32_t *__restrict__ vis, uint32_t *__restrict__ fr) {
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= Q) return;
-  int s = seeds[q];
-  if (s < 0 || s >= N) return;  // the reference would raise an index error; the row stays -1
-  geo[(size_t)q * N + s] = 0.f;  // geodesic_utils.py:118
-  int si = rank ? rank[s] : s;
-  atomicOr(vis + (size_t)si * W + (q >> 5), 1u << (q & 31));  // :119
-  atomicOr(fr + (size_t)si * W + (q >> 5), 1u << (q & 31));
-}
-
-// ---- the level loop -----------------------------------------------------------------------------------
-// flags[0..2]: rotating "this level reached something" flags; stats[0] reached pairs, stats[1] levels run
-__global__ void __launch_bounds__(256)
-    geo_levels_kernel(int N, int W, int Wshift, int Q, int max_step, const int *__restrict__ rev_start,
-                      const uint2 *__restrict__ rev, const int *__restrict__ order, uint32_t *vis, uint32_t *fr0,
-                      uint32_t *fr1, float *geo, int *flags, unsigned long long *stats) {
-  cg::grid_group grid = cg::this_grid();
-  const size_t total = (size_t)N << Wshift;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t tid0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  uint32_t *cur = fr0, *nxt = fr1;
-  __shared__ int s_any;
-  __shared__ unsigned long long s_cnt;
-  for (int level = 1; level <= max_step; ++level) {
-    if (threadIdx.x == 0) {
-      s_any = 0;
-      s_cnt = 0ull;
-    }
-    __syncthreads();
-    unsigned cnt = 0;
-    for (size_t gid = tid0; gid < total; gid += stride) {
-      const int t = (int)(gid >> Wshift), w = (int)(gid & (W - 1));
-      const int qbase = w << 5;
-      uint32_t qmask = qbase + 32 <= Q ? 0xffffffffu : (qbase < Q ? ((1u << (Q - qbase)) - 1u) : 0u);
-      const uint32_t vold = vis[gid];
-      // level 1 ignores the visited set (geodesic_utils.py:123 has no visited filter)
-      uint32_t avail = (level == 1 ? 0xffffffffu : ~vold) & qmask;
-      uint32_t newb = 0u;
-      if (avail) {
-        const int e0 = __ldg(rev_start + t), e1 = __ldg(rev_start + t + 1);
-        const int to = order ? __ldg(order + t) : t;
-        for (int e = e0; e < e1 && avail; ++e) {
-          const uint2 en = __ldg(rev + e);
-          uint32_t nb = cur[((size_t)en.x << Wshift) + w] & avail;
-          if (nb) {
-            avail &= ~nb;
-            newb |= nb;
-            const float wgt = __uint_as_float(en.y);
-            const int po = order ? __ldg(order + en.x) : (int)en.x;
-            do {
-              int b = __ffs(nb) - 1;
-              nb &= nb - 1;
-              size_t rowq = (size_t)(qbase + b) * N;
-              // level 1: the candidate distance is the edge itself (:127); later: edge + parent (:144)
-              float d = level == 1 ? wgt : __fadd_rn(wgt, geo[rowq + po]);
-              geo[rowq + to] = d;  // :139
-            } while (nb);
+        for (int u = 0; u < GEO_UNROLL; ++u) {
+          const size_t at = (size_t)pe[u].x * k + 1 + slot[u];
+          t[u] = ok[u] ? (IS64 ? ((const long long *)a.I)[at] : (long long)((const int *)a.I)[at]) : -1;
+          w[u] = ok[u] ? __ldg(a.D + at) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < GEO_UNROLL; ++u) {
+          bool go = ok[u] && (w[u] <= radius) && t[u] >= 0 && t[u] < N;  // :123 / :151
+          if (go) {
+            if (a.bitmap_words)
+              go = !(vis[t[u] >> 5] & (1u << (t[u] & 31)));
+            else
+              go = ld_cg_u32(rowu + t[u]) >= GEO_KEYBIT;
+          }
+          const uint32_t key = GEO_KEYBIT | ((uint32_t)pe[u].x << a.slot_bits) | (uint32_t)slot[u];
+          if (go) atomicMin(rowu + t[u], key);
+          const int pos = warp_append_pos(go, &s_surv_n);
+          if (go && pos < GEO_SCAP) {
+            sv_t[pos] = (int)t[u];
+            sv_key[pos] = key;
+            // level 1: the distance is the edge itself (:127); later: edge + parent's distance (:144)
+            sv_d[pos] = __float_as_int(level == 1 ? w[u] : __fadd_rn(w[u], __int_as_float(pe[u].y)));
           }
         }
       }
-      nxt[gid] = newb;
-      if (newb) {
-        vis[gid] = vold | newb;  // :140
-        cnt += __popc(newb);
+      __syncthreads();
+      const int nsurv = s_surv_n;
+      // ---- pass B: the claimant whose key survived is the reference's winner --------------------------
+      if (nsurv <= GEO_SCAP) {
+        for (int wi0 = tid & ~31; wi0 < nsurv; wi0 += GEO_THREADS * GEO_UNROLL) {
+          const int i0 = wi0 + (tid & 31);
+          uint32_t cur[GEO_UNROLL];
+#pragma unroll
+          for (int u = 0; u < GEO_UNROLL; ++u) {
+            const int i = i0 + u * GEO_THREADS;
+            cur[u] = i < nsurv ? ld_cg_u32(rowu + sv_t[i]) : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < GEO_UNROLL; ++u) {
+            const int i = i0 + u * GEO_THREADS;
+            const bool win = i < nsurv && cur[u] == sv_key[i];
+            int tt = 0, dd = 0;
+            if (win) {
+              tt = sv_t[i], dd = sv_d[i];
+              rowu[tt] = (uint32_t)dd;  // :139
+              if (a.bitmap_words) atomicOr(vis + (tt >> 5), 1u << (tt & 31));  // :140
+            }
+            const int pos = warp_append_pos(win, &s_next_n);
+            if (win) {
+              if (pos < GEO_QCAP)
+                nq[pos] = make_int2(tt, dd);
+              else
+                ovf[ovf_index(pos, level & 1, N)] = make_int2(tt, dd);
+            }
+          }
+        }
+      } else {
+        // more claimants than the on-chip list holds: walk the candidates again (same tests as pass A)
+        for (long long c = tid; c < ncand; c += GEO_THREADS) {
+          const int node = (int)(c >> a.slot_bits), sl = (int)(c & (KP - 1));
+          if (sl >= K) continue;
+          const int2 p1 = frontier_get(fq, ovf, node, par, N);
+          const size_t at = (size_t)p1.x * k + 1 + sl;
+          const long long t1 = IS64 ? ((const long long *)a.I)[at] : (long long)((const int *)a.I)[at];
+          const float w1 = __ldg(a.D + at);
+          if (!(w1 <= radius) || t1 < 0 || t1 >= N) continue;
+          if (a.bitmap_words && (vis[t1 >> 5] & (1u << (t1 & 31)))) continue;
+          const uint32_t key = GEO_KEYBIT | ((uint32_t)p1.x << a.slot_bits) | (uint32_t)sl;
+          if (ld_cg_u32(rowu + t1) != key) continue;
+          const float d = level == 1 ? w1 : __fadd_rn(w1, __int_as_float(p1.y));
+          row[t1] = d;
+          if (a.bitmap_words) atomicOr(vis + (t1 >> 5), 1u << (t1 & 31));
+          const int pos = atomicAdd(&s_next_n, 1);
+          const int2 ne = make_int2((int)t1, __float_as_int(d));
+          if (pos < GEO_QCAP)
+            nq[pos] = ne;
+          else
+            ovf[ovf_index(pos, level & 1, N)] = ne;
+        }
       }
+      __syncthreads();
+      const int nextF = s_next_n;
+      if (level == 1 && tid == 0) {
+        // the seed joins the visited set now; if no self edge re-won it, its distance stays 0
+        if (ld_cg_u32(rowu + s) == GEO_UNVISITED) row[s] = 0.f;
+        if (a.bitmap_words) atomicOr(vis + (s >> 5), 1u << (s & 31));
+      }
+      if (nextF > 0 && level > deepest) deepest = level;
+      __syncthreads();
+      if (tid == 0) {
+        s_reached += (unsigned long long)nextF;
+        s_next_n = 0;
+        s_surv_n = 0;
+      }
+      F = nextF;
+      int2 *tq = fq;
+      fq = nq;
+      nq = tq;
     }
-    if (cnt) {
-      s_any = 1;
-      atomicAdd(&s_cnt, (unsigned long long)cnt);
-    }
+    if (level == 0 && seed_ok && tid == 0) row[s] = 0.f;  // max_step <= 0: only the seed entry (:118)
     __syncthreads();
-    if (threadIdx.x == 0) {
-      if (s_any) {
-        flags[level % 3] = 1;
-        atomicAdd(stats, s_cnt);
-      }
-      if (blockIdx.x == 0) flags[(level + 1) % 3] = 0;
-    }
-    grid.sync();
-    const int any = *(volatile int *)(flags + level % 3);
-    if (!any) break;  // geodesic_utils.py:156-157
-    if (blockIdx.x == 0 && threadIdx.x == 0) stats[1] = (unsigned long long)level;
-    uint32_t *tmp = cur;
-    cur = nxt;
-    nxt = tmp;
+    if (tid == 0) reached_total += s_reached;
+  }
+  if (tid == 0) {
+    if (reached_total) atomicAdd(a.stats, reached_total);
+    atomicMax(a.stats + 1, (unsigned long long)deepest);
   }
 }
 
+static int ceil_log2(int v) {
+  int b = 0;
+  while ((1 << b) < v) ++b;
+  return b;
+}
+
+struct GeoPlan {
+  int grid, bitmap_words;
+  size_t smem;
+};
+
+// shared-memory plan, identical for sizing and launching: 227 KB usable per CTA and per SM on sm_100
+static void geo_smem_plan(int N, int *bitmap_words, size_t *smem, int *ctas_per_sm) {
+  const size_t queues = sizeof(int2) * 2 * GEO_QCAP + 12 * (size_t)GEO_SCAP;
+  int words = (N + 31) / 32;
+  size_t bytes = queues + sizeof(uint32_t) * (size_t)words;
+  if (bytes > (size_t)226 * 1024) {  // scene too large for an on-chip bitmap: test the output row instead
+    words = 0;
+    bytes = queues;
+  }
+  int per_sm = (int)((size_t)(227 * 1024) / (bytes + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;  // 4 x 512 threads = the SM's 2048
+  *bitmap_words = words;
+  *smem = bytes;
+  *ctas_per_sm = per_sm;
+}
+
+static int plan_geo(int N, int Q, GeoPlan *p) {
+  int per_sm = 1;
+  geo_smem_plan(N, &p->bitmap_words, &p->smem, &per_sm);
+  static int bps_cap = -1;
+  if (bps_cap < 0) {
+    const char *e = getenv("GF_GEO_BPS");  // experiment knob
+    bps_cap = e ? atoi(e) : 0;
+  }
+  if (bps_cap > 0 && per_sm > bps_cap) per_sm = bps_cap;
+  int grid = num_sms() * per_sm;
+  if (grid > Q) grid = Q;
+  p->grid = grid < 1 ? 1 : grid;
+  return GF_OK;
+}
+
 size_t geodesic_workspace_bytes(int N, int k, int Q) {
-  int Qc = Q < GEO_MAX_Q_PER_PASS ? Q : GEO_MAX_Q_PER_PASS;
-  int W = 1;
-  while (W * 32 < Qc) W <<= 1;
-  size_t K = k > 1 ? (size_t)(k - 1) : 0;
+  (void)k;
+  int words = 0, per_sm = 1;
+  size_t smem = 0;
+  geo_smem_plan(N, &words, &smem, &per_sm);
+  long long grid = (long long)num_sms() * per_sm;
+  if (grid > Q) grid = Q;
+  if (grid < 1) grid = 1;
   size_t b = 0;
-  b += align256(sizeof(int) * ((size_t)N + 1)) * 3;               // rev_count, rev_start, cursor
-  b += align256(sizeof(unsigned long long) * ((size_t)N * K + 1));  // rev entries
-  b += align256(sizeof(uint32_t) * (size_t)N * W) * 3;             // vis, fr0, fr1
-  b += align256(sizeof(int) * SCAN_BLOCKS);
-  b += align256(64);  // flags
-  b += align256(64);  // internal stats
+  b += align256(sizeof(int2) * ((size_t)N + 2) * (size_t)grid);  // frontier overflow
+  b += align256(64);                                             // seed counter
+  b += align256(64);                                             // stats
   return b + 1024;
 }
 
 int geodesic_run(const float *D, const void *I, int is64, int N, int k, const int *seeds, int Q, float radius,
-                 int max_step, float *geo, const int *order, const int *rank, int64_t *stats_out, void *workspace,
-                 size_t workspace_bytes, cudaStream_t st) {
+                 int max_step, float *geo, int64_t *stats_out, void *workspace, size_t workspace_bytes,
+                 cudaStream_t st) {
   const int K = k - 1;
-  int Qc0 = Q < GEO_MAX_Q_PER_PASS ? Q : GEO_MAX_Q_PER_PASS;
-  int W = 1, Wshift = 0;
-  while (W * 32 < Qc0) W <<= 1, ++Wshift;
+  GeoPlan p;
+  int rc = plan_geo(N, Q, &p);
+  if (rc) return rc;
+  const int slot_bits = ceil_log2(K > 1 ? K : 1);
+  if (((unsigned long long)N << slot_bits) >= GEO_KEYMAX) {
+    set_error("geodesic: N=%d with k=%d does not fit the 30-bit claim key (N << %d must be < 2^30)", N, k, slot_bits);
+    return GF_ERR_INVALID;
+  }
   Arena a(workspace, workspace_bytes);
-  int *rev_count = a.take<int>((size_t)N + 1);
-  int *rev_start = a.take<int>((size_t)N + 1);
-  int *cursor = a.take<int>((size_t)N + 1);
-  unsigned long long *rev = a.take<unsigned long long>((size_t)N * (K > 0 ? K : 0) + 1);
-  uint32_t *vis = a.take<uint32_t>((size_t)N * W);
-  uint32_t *fr0 = a.take<uint32_t>((size_t)N * W);
-  uint32_t *fr1 = a.take<uint32_t>((size_t)N * W);
-  int *bsum = a.take<int>(SCAN_BLOCKS);
-  int *flags = a.take<int>(16);
+  int2 *overflow = a.take<int2>(((size_t)N + 2) * (size_t)p.grid);
+  unsigned *counter = a.take<unsigned>(16);
   unsigned long long *stats = a.take<unsigned long long>(8);
   if (!a.ok) {
     set_error("geodesic: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
               geodesic_workspace_bytes(N, k, Q));
     return GF_ERR_WORKSPACE;
   }
-  const int nb = num_sms() * 8;
+  GF_CUDA(cudaMemsetAsync(counter, 0, 64, st));
   GF_CUDA(cudaMemsetAsync(stats, 0, 64, st));
-  // reverse CSR (once per scene)
-  GF_CUDA(cudaMemsetAsync(rev_count, 0, sizeof(int) * ((size_t)N + 1), st));
-  GF_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * ((size_t)N + 1), st));
-  const long long nedge = (long long)N * K;
-  if (nedge > 0) {
-    int g = (int)((nedge + 255) / 256 < nb ? (nedge + 255) / 256 : nb);
-    geo_count_edges_kernel<<<g, 256, 0, st>>>(D, I, is64, N, k, radius, rank, rev_count);
-    GF_LAUNCHED();
+  stage_mark(ST_GEO_READY, st);
+  GeoArgs ga;
+  ga.D = D, ga.I = I, ga.N = N, ga.k = k, ga.Q = Q, ga.max_step = max_step, ga.radius = radius;
+  ga.seeds = seeds, ga.geo = geo, ga.overflow = overflow, ga.seed_counter = counter, ga.stats = stats;
+  ga.bitmap_words = p.bitmap_words, ga.slot_bits = slot_bits;
+  if (is64) {
+    GF_CUDA(cudaFuncSetAttribute(geo_seed_bfs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    geo_seed_bfs_kernel<true><<<p.grid, GEO_THREADS, p.smem, st>>>(ga);
+  } else {
+    GF_CUDA(cudaFuncSetAttribute(geo_seed_bfs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    geo_seed_bfs_kernel<false><<<p.grid, GEO_THREADS, p.smem, st>>>(ga);
   }
-  int rc = exclusive_scan(rev_count, N, rev_start, bsum, st);
-  if (rc) return rc;
-  if (nedge > 0) {
-    int g = (int)((nedge + 255) / 256 < nb ? (nedge + 255) / 256 : nb);
-    geo_fill_edges_kernel<<<g, 256, 0, st>>>(D, I, is64, N, k, radius, rank, rev_start, cursor, rev);
-    GF_LAUNCHED();
-    geo_sort_rows_kernel<<<(N + 127) / 128 < nb ? (N + 127) / 128 : nb, 128, 0, st>>>(D, N, k, rank, rev_start, rev);
-    GF_LAUNCHED();
-  }
-  // output fill (geodesic_utils.py:113)
-  {
-    size_t n = (size_t)Q * N;
-    geo_fill_kernel<<<num_sms() * 16, 256, 0, st>>>(geo, n, -1.0f);
-    GF_LAUNCHED();
-  }
-  // cooperative launch geometry
-  static int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, geo_levels_kernel, 256, 0));
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-  }
-  for (int q0 = 0; q0 < Q; q0 += GEO_MAX_Q_PER_PASS) {
-    const int Qc = Q - q0 < GEO_MAX_Q_PER_PASS ? Q - q0 : GEO_MAX_Q_PER_PASS;
-    GF_CUDA(cudaMemsetAsync(vis, 0, sizeof(uint32_t) * (size_t)N * W, st));
-    GF_CUDA(cudaMemsetAsync(fr0, 0, sizeof(uint32_t) * (size_t)N * W, st));
-    GF_CUDA(cudaMemsetAsync(flags, 0, 64, st));
-    float *geo_c = geo + (size_t)q0 * N;
-    geo_seed_kernel<<<(Qc + 127) / 128, 128, 0, st>>>(seeds + q0, Qc, N, W, rank, geo_c, vis, fr0);
-    GF_LAUNCHED();
-    if (q0 == 0) stage_mark(ST_GEO_READY, st);
-    if (max_step > 0 && K > 0) {
-      size_t total = (size_t)N * W;
-      int grid = num_sms() * blocks_per_sm;
-      size_t want = (total + 255) / 256;
-      if ((size_t)grid > want) grid = (int)(want > 0 ? want : 1);
-      const uint2 *rev2 = (const uint2 *)rev;
-      unsigned long long *st_ptr = stats;
-      int Nn = N, Ww = W, Ws = Wshift, Qq = Qc, ms = max_step;
-      void *args[] = {&Nn, &Ww, &Ws, &Qq, &ms, &rev_start, &rev2, &order, &vis, &fr0, &fr1, &geo_c, &flags, &st_ptr};
-      GF_CUDA(cudaLaunchCooperativeKernel((const void *)geo_levels_kernel, dim3(grid), dim3(256), args, 0, st));
-      count_launch();
-    }
-  }
+  GF_LAUNCHED();
   stage_mark(ST_GEO_DONE, st);
   if (stats_out) GF_CUDA(cudaMemcpyAsync(stats_out, stats, 16, cudaMemcpyDeviceToDevice, st));
   return GF_OK;
@@ -384,13 +374,12 @@ extern "C" size_t gf_geodesic_workspace_bytes(int N, int k, int Q) {
 }
 
 extern "C" int gf_geodesic(const float *knn_dist, const void *knn_idx, int idx_is_i64, int N, int k, const int *seeds,
-                           int Q, float radius, int max_step, float *geo, const int *order, const int *rank,
-                           int64_t *stats, void *workspace, size_t workspace_bytes, void *stream) {
+                           int Q, float radius, int max_step, float *geo, int64_t *stats, void *workspace,
+                           size_t workspace_bytes, void *stream) {
   GF_CHECK_ARG(N >= 0 && Q >= 0, "geodesic: negative size");
   GF_CHECK_ARG(k >= 1 && k <= 256, "geodesic: k=%d outside [1,256]", k);
-  GF_CHECK_ARG((order == nullptr) == (rank == nullptr), "geodesic: order and rank must be given together");
   if (N == 0 || Q == 0) return GF_OK;
   GF_CHECK_ARG(knn_dist && knn_idx && seeds && geo, "geodesic: null pointer");
-  return geodesic_run(knn_dist, knn_idx, idx_is_i64, N, k, seeds, Q, radius, max_step, geo, order, rank, stats,
-                      workspace, workspace_bytes, (cudaStream_t)stream);
+  return geodesic_run(knn_dist, knn_idx, idx_is_i64, N, k, seeds, Q, radius, max_step, geo, stats, workspace,
+                      workspace_bytes, (cudaStream_t)stream);
 }

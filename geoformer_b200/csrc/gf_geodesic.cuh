@@ -4,11 +4,9 @@
 
 namespace gf {
 
-constexpr int GEO_MAX_Q_PER_PASS = 1024;  // 32 seed words per point = one warp per target row
-
 size_t geodesic_workspace_bytes(int N, int k, int Q);
 int geodesic_run(const float *D, const void *I, int is64, int N, int k, const int *seeds, int Q, float radius,
-                 int max_step, float *geo, const int *order, const int *rank, int64_t *stats_out, void *workspace,
-                 size_t workspace_bytes, cudaStream_t st);
+                 int max_step, float *geo, int64_t *stats_out, void *workspace, size_t workspace_bytes,
+                 cudaStream_t st);
 
 }  // namespace gf

@@ -2,8 +2,7 @@
 // scene (what GeoFormerFS.forward does at geoformer_fs.py:630-645 + :497-506 through three separate
 // libraries and a Python loop).  FPS (a <= 16-SM cluster kernel, latency bound) runs on a forked
 // stream concurrently with the kNN graph construction (which fills the other SMs); the geodesic
-// waits for both.  The grid order of the kNN build is handed to the geodesic as its internal point
-// numbering.
+// waits for both.
 #include "gf_geodesic.cuh"
 #include "gf_knn.cuh"
 
@@ -100,8 +99,7 @@ static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, in
   // join, then propagate
   if (!seeds_given) GF_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   stage_mark(ST_KNN_DONE, st);
-  return geodesic_run(dist, idx, /*is64=*/0, N, k, seeds, Q, radius, max_step, geo, gb.order, gb.rank, stats, ws_geo,
-                      p.geo, st);
+  return geodesic_run(dist, idx, /*is64=*/0, N, k, seeds, Q, radius, max_step, geo, stats, ws_geo, p.geo, st);
 }
 
 extern "C" int gf_guidance(const float *xyz, int N, int Q, int k, float radius, int max_step, int *seeds, float *geo,

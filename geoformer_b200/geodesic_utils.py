@@ -113,14 +113,14 @@ def geodesic_from_graph(D, I, seeds, radius, max_step, return_stats=False):
         nbytes = L.gf_geodesic_workspace_bytes(N, k, Q)
         ws = C.workspace.get(D.device, "geodesic", nbytes) if nbytes else None
         C.check(L.gf_geodesic(C.ptr(D), C.ptr(I), 1 if I.dtype == torch.int64 else 0, N, k, C.ptr(seeds), Q,
-                              ctypes.c_float(float(radius)), int(max_step), C.ptr(geo), None, None, C.ptr(stats),
+                              ctypes.c_float(float(radius)), int(max_step), C.ptr(geo), C.ptr(stats),
                               C.ptr(ws), nbytes, C.stream_of(D.device)), "geodesic")
     return (geo, stats) if return_stats else geo
 
 
 def geodesic_from_points(locs, seeds, neighbor, radius, max_step, return_graph=False, return_stats=False):
     """kNN graph + propagation of one scene in one library call (the body of the reference loop,
-    geodesic_utils.py:98-163) with the kNN grid order reused as the propagation's point numbering."""
+    geodesic_utils.py:98-163)."""
     C.check_cuda_f32(locs, "locs")
     N = locs.size(0)
     seeds = seeds.to(device=locs.device, dtype=torch.int32).contiguous()

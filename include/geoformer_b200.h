@@ -43,8 +43,8 @@ void gf_reset_launch_count(void);
 
 /* Profiling hook: `events` = up to 5 cudaEvent_t (as void*) recorded, during the NEXT gf_guidance* /
  * gf_geodesic call of this thread only, on the launching stream at: [0] entry, [1] kNN grid built,
- * [2] kNN graph done (and FPS joined), [3] reverse CSR + state ready (just before the level kernel),
- * [4] level kernel done.  NULL / 0 disarms.                                                       */
+ * [2] kNN graph done (and FPS joined), [3] just before the propagation kernel, [4] propagation
+ * kernel done.  NULL / 0 disarms.                                                                 */
 int gf_set_stage_events(void **events, int n);
 void *gf_event_create(void);                     /* cudaEventCreate, NULL on failure */
 void gf_event_destroy(void *event);
@@ -103,13 +103,12 @@ int gf_knn(const float *xyz, int N, const float *queries, int nq, int k, int sqr
 /* One scene.  knn_dist (N,k) f32 (sqrt'ed), knn_idx (N,k) i64 or i32 (idx_is_i64), column 0 is
  * dropped like the reference (:110-111).  seeds (Q) i32.  geo (Q,N) f32, -1 = unreachable.
  * Level-synchronous first-visit BFS; within a level the parent with the smallest index, then the
- * smallest neighbour slot, wins.  order/rank (N) i32: optional spatial renumbering
- * (order[internal] = original, rank[original] = internal); NULL = identity.
- * stats (2) i64 device, optional: [0] = reached (q,p) pairs, [1] = levels executed.             */
+ * smallest neighbour slot, wins.  Needs N << ceil(log2(k-1)) < 2^30.
+ * stats (2) i64 device, optional: [0] = reached (q,p) pairs, [1] = deepest level reached.        */
 size_t gf_geodesic_workspace_bytes(int N, int k, int Q);
 int gf_geodesic(const float *knn_dist, const void *knn_idx, int idx_is_i64, int N, int k, const int *seeds, int Q,
-                float radius, int max_step, float *geo, const int *order, const int *rank, int64_t *stats,
-                void *workspace, size_t workspace_bytes, void *stream);
+                float radius, int max_step, float *geo, int64_t *stats, void *workspace, size_t workspace_bytes,
+                void *stream);
 
 /* ---- distance -> bias epilogues ------------------------------------------------------------- */
 
