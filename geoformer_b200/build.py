@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
                 and os.path.getmtime(obj) > hdr):
             return obj, ""
-        cmd = [_nvcc()] + ccbin + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [_nvcc()] + ccbin + NVCC_FLAGS + os.environ.get("GF_NVCC_EXTRA", "").split() + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
