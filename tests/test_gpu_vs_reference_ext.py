@@ -1,0 +1,134 @@
+"""GPU tests against the reference's OWN pointnet2 CUDA kernels (oracle/_ref, built unmodified from the
+reference sources).  Three-way check on the same inputs: reference kernels == CPU oracle == our kernels.
+Skipped when oracle/_ref was not built (it is built by __graft_entry__.build() wherever /root/reference
+exists and travels to the GPU box as a prebuilt .so)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from geoformer_b200.scenes import scene  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ref_ext():
+    from oracle.build_ref import load_ref_ext
+
+    ext = load_ref_ext()
+    if ext is None:
+        pytest.skip("oracle/_ref (reference pointnet2 CUDA build) not present")
+    return ext
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_lib):
+    return torch.device("cuda:0")
+
+
+def _lattice(n, seed):
+    g = np.random.default_rng(seed)
+    x = g.integers(-3, 4, size=(n, 3)).astype(np.float32) * 0.25
+    x[g.integers(0, n, size=max(1, n // 50))] = 0.0
+    x[g.integers(0, n, size=max(1, n // 50))] = np.float32(0.01)
+    return x
+
+
+@pytest.mark.parametrize("kind,N,m", [("scene", 20000, 512), ("scene", 100000, 256), ("lattice", 4096, 512),
+                                      ("lattice", 513, 300), ("lattice", 64, 64), ("scene", 1000, 999),
+                                      ("lattice", 9000, 256)])
+def test_fps_three_way(ref_ext, oracle_lib, dev, kind, N, m):
+    from geoformer_b200.pointnet2 import _ext
+
+    xyz = (scene(N, 5).numpy() if kind == "scene" else _lattice(N, N))[None]
+    ref = ref_ext.furthest_point_sampling(torch.from_numpy(xyz).to(dev), m).cpu().numpy()
+    ours = _ext.furthest_point_sampling(torch.from_numpy(xyz).to(dev), m).cpu().numpy()
+    assert np.array_equal(ours, ref), "our FPS differs from the reference kernel"
+    if N * m <= 30_000_000:
+        assert np.array_equal(oracle_lib.furthest_point_sampling(xyz, m), ref), "oracle differs from the reference kernel"
+
+
+def test_ball_query_group_gather_three_way(ref_ext, oracle_lib, dev):
+    from geoformer_b200.pointnet2 import _ext
+
+    xyz = scene(30000, 7)[None]
+    centres = xyz[:, torch.randperm(30000, generator=torch.Generator().manual_seed(2))[:2048]].contiguous()
+    centres[0, 0] += 100.0
+    feats = torch.randn(1, 16, 30000, generator=torch.Generator().manual_seed(1))
+    for r, ns in ((0.2, 64), (0.05, 16), (1.5, 8)):
+        ref = ref_ext.ball_query(centres.to(dev), xyz.to(dev), r, ns)
+        ours = _ext.ball_query(centres.to(dev), xyz.to(dev), r, ns)
+        assert torch.equal(ours, ref)
+        assert np.array_equal(oracle_lib.ball_query(centres.numpy(), xyz.numpy(), r, ns), ref.cpu().numpy())
+    assert torch.equal(_ext.group_points(feats.to(dev), ours), ref_ext.group_points(feats.to(dev), ref))
+    sel = ref[:, :, 0].contiguous()
+    assert torch.equal(_ext.gather_points(feats.to(dev), sel), ref_ext.gather_points(feats.to(dev), sel))
+    go = torch.randn(1, 16, 2048, 8, generator=torch.Generator().manual_seed(3)).to(dev)
+    torch.testing.assert_close(_ext.group_points_grad(go, ref, 30000), ref_ext.group_points_grad(go, ref, 30000),
+                               rtol=1e-4, atol=1e-4)  # fp32 atomic order differs run to run in both
+    go2 = torch.randn(1, 16, 2048, generator=torch.Generator().manual_seed(4)).to(dev)
+    torch.testing.assert_close(_ext.gather_points_grad(go2, sel, 30000), ref_ext.gather_points_grad(go2, sel, 30000),
+                               rtol=1e-4, atol=1e-4)
+
+
+def test_three_nn_interpolate_three_way(ref_ext, oracle_lib, dev):
+    from geoformer_b200.pointnet2 import _ext
+
+    g = torch.Generator().manual_seed(5)
+    unknown, known = scene(5000, 11)[None].to(dev), scene(2000, 12)[None].to(dev)
+    rd2, ridx = ref_ext.three_nn(unknown, known)
+    d2, idx = _ext.three_nn(unknown, known)
+    assert torch.equal(idx, ridx) and torch.equal(d2, rd2)
+    od2, oidx = oracle_lib.three_nn(unknown.cpu().numpy(), known.cpu().numpy())
+    assert np.array_equal(oidx, ridx.cpu().numpy()) and np.array_equal(od2, rd2.cpu().numpy())
+    feats = torch.randn(1, 8, 2000, generator=g).to(dev)
+    w = torch.rand(1, 5000, 3, generator=g).to(dev)
+    ref = ref_ext.three_interpolate(feats, ridx, w)
+    assert torch.equal(_ext.three_interpolate(feats, idx, w), ref)
+    assert np.array_equal(oracle_lib.three_interpolate(feats.cpu().numpy(), oidx, w.cpu().numpy()), ref.cpu().numpy())
+    go = torch.randn(1, 8, 5000, generator=g).to(dev)
+    torch.testing.assert_close(_ext.three_interpolate_grad(go, idx, w, 2000),
+                               ref_ext.three_interpolate_grad(go, ridx, w, 2000), rtol=1e-4, atol=1e-4)
+
+
+def test_reference_python_surface_runs_on_our_ext(ref_ext, dev):
+    """QueryAndGroup / group_points chain: our Python surface on our operators == the same chain on the
+    reference operators (the reference's own pointnet2_utils.py cannot travel to the GPU box)."""
+    from geoformer_b200 import pointnet2_utils as pu
+
+    x = scene(20000, 3)[None].to(dev)
+    feats = torch.randn(1, 16, 20000, generator=torch.Generator().manual_seed(0)).to(dev)
+    grouper = pu.QueryAndGroup(0.2, 64, use_xyz=True, ret_grouped_xyz=True, normalize_xyz=True)
+    new_xyz, gfeat, gxyz, inds = pu.group_points(x, feats, grouper, 2048)
+    r_inds = ref_ext.furthest_point_sampling(x, 2048)
+    assert torch.equal(inds, r_inds)
+    r_new = ref_ext.gather_points(x.transpose(1, 2).contiguous(), r_inds).transpose(1, 2).contiguous()
+    assert torch.equal(new_xyz, r_new)
+    r_idx = ref_ext.ball_query(r_new, x, 0.2, 64)
+    r_gx = ref_ext.group_points(x.transpose(1, 2).contiguous(), r_idx)
+    r_gx -= r_new.transpose(1, 2).unsqueeze(-1)
+    r_gx /= 0.2
+    assert torch.equal(gxyz, r_gx)
+    assert torch.equal(gfeat[:, 3:], ref_ext.group_points(feats, r_idx))
+
+
+def test_golden_geodesic_fixtures_on_gpu(dev):
+    """the committed outputs of the reference's own cal_geodesic_vectorize (tests/golden/make_golden.py)"""
+    import glob
+    import os
+
+    from geoformer_b200.geodesic_utils import FlatL2Index, cal_geodesic_vectorize, geodesic_from_graph
+
+    paths = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "geodesic_*.npz")))
+    assert paths
+    for path in paths:
+        g = np.load(path)
+        N = g["xyz"].shape[0]
+        geo = geodesic_from_graph(torch.from_numpy(g["knn_dist"]).to(dev), torch.from_numpy(g["knn_idx"]).to(dev),
+                                  torch.from_numpy(g["seeds"]).to(dev), float(g["radius"]), int(g["max_step"]))
+        assert np.array_equal(geo.cpu().numpy(), g["geo"]), path
+        out = cal_geodesic_vectorize(FlatL2Index(), torch.from_numpy(g["seeds"][None]).to(dev),
+                                     torch.from_numpy(g["xyz"]).to(dev), torch.tensor([0, N], dtype=torch.int32),
+                                     max_step=int(g["max_step"]), neighbor=int(g["k"]), radius=float(g["radius"]),
+                                     n_queries=len(g["seeds"]))
+        assert np.array_equal(out[0].cpu().numpy(), g["geo"]), path
