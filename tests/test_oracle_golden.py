@@ -126,3 +126,40 @@ def test_oracle_geodesic_level_semantics(oracle_lib):
     assert geo2.tolist() == [0.0, 1.0, 1.5, 2.0, 2.5, -1.0]
     geo3 = oracle_lib.geodesic(D, I, np.array([0]), 1.2, 10)[0]  # the 1.5 edge is outside the radius
     assert geo3.tolist() == [0.0, 1.0, -1.0, 2.0, -1.0, 3.0]
+
+
+# ---- fixtures produced by the reference's own CUDA kernels on the GPU box ----------------------------
+# (tests/golden/make_golden_ref_ext.py; oracle/_ref = lib/pointnet2/_ext_src compiled unmodified)
+@pytest.fixture(scope="module")
+def ref_ext_golden():
+    path = os.path.join(GOLD, "ref_ext_golden.npz")
+    if not os.path.exists(path):
+        pytest.skip("ref_ext_golden.npz not generated yet")
+    return np.load(path)
+
+
+def test_oracle_fps_matches_reference_kernel_fixture(oracle_lib, ref_ext_golden):
+    g = ref_ext_golden
+    names = sorted(k[4:-4] for k in g.files if k.startswith("fps_") and k.endswith("_idx"))
+    assert len(names) >= 6
+    for name in names:
+        xyz, m, idx = g["fps_%s_xyz" % name], int(g["fps_%s_m" % name]), g["fps_%s_idx" % name]
+        assert np.array_equal(oracle_lib.furthest_point_sampling(xyz, m), idx), name
+
+
+def test_oracle_ball_query_group_gather_match_reference_kernel_fixture(oracle_lib, ref_ext_golden):
+    g = ref_ext_golden
+    for tag in ("a", "b"):
+        out = oracle_lib.ball_query(g["bq_centres"], g["bq_xyz"], float(g["bq_%s_r" % tag]), int(g["bq_%s_ns" % tag]))
+        assert np.array_equal(out, g["bq_%s_idx" % tag]), tag
+    assert np.array_equal(oracle_lib.group_points(g["grp_feats"], g["bq_a_idx"]), g["grp_out"])
+    assert np.array_equal(oracle_lib.gather_points(g["grp_feats"], np.ascontiguousarray(g["bq_a_idx"][:, :, 0])), g["gat_out"])
+
+
+def test_oracle_three_nn_interpolate_match_reference_kernel_fixture(oracle_lib, ref_ext_golden):
+    g = ref_ext_golden
+    d2, idx = oracle_lib.three_nn(g["tnn_unknown"], g["tnn_known"])
+    assert np.array_equal(idx, g["tnn_idx"]) and np.array_equal(d2, g["tnn_d2"])
+    assert np.array_equal(oracle_lib.three_interpolate(g["ti_feats"], idx, g["ti_w"]), g["ti_out"])
+    d2s, idxs = oracle_lib.three_nn(g["tnn_unknown"][:, :10], g["tnn_known"][:, :2])
+    assert np.array_equal(idxs, g["tnn_small_idx"]) and np.array_equal(d2s, g["tnn_small_d2"])
