@@ -77,3 +77,41 @@ def test_ops_fail_loudly_on_cpu_tensors(cuda_lib):
     with pytest.raises(RuntimeError):
         cal_geodesic_vectorize(None, torch.zeros(1, 4, dtype=torch.int32), torch.zeros(8, 3),
                                torch.tensor([0, 8], dtype=torch.int32), n_queries=2, neighbor=2)
+
+
+def test_reference_pointnet2_utils_imports_on_top_of_our_ext():
+    """drop-in check (build container only): the reference's own lib/pointnet2/pointnet2_utils.py imports
+    unchanged once `pointnet2._ext` is aliased to ours, and finds the nine operators it calls."""
+    import importlib
+    import sys
+
+    import pytest
+
+    if not os.path.isdir("/root/reference/lib/pointnet2"):
+        pytest.skip("reference tree not present (GPU box)")
+    import geoformer_b200.pointnet2 as p2
+
+    saved = {k: sys.modules.get(k) for k in ("pointnet2", "pointnet2._ext")}
+    sys.modules["pointnet2"], sys.modules["pointnet2._ext"] = p2, p2._ext
+    sys.path.insert(0, "/root/reference")
+    try:
+        mod = importlib.import_module("lib.pointnet2.pointnet2_utils")
+        assert mod._ext is p2._ext
+        for name in ("furthest_point_sampling", "gather_points", "gather_points_grad", "three_nn", "three_interpolate",
+                     "three_interpolate_grad", "ball_query", "group_points", "group_points_grad"):
+            assert callable(getattr(mod._ext, name)), name
+        for name in ("furthest_point_sample", "gather_operation", "three_nn", "three_interpolate", "grouping_operation",
+                     "ball_query", "QueryAndGroup", "GroupAll"):
+            assert hasattr(mod, name)
+        import geoformer_b200.pointnet2_utils as ours
+
+        assert {n for n in dir(mod) if n[0].isupper() and n not in ("Function",)} <= set(dir(ours)) | {"RandomDropout"}
+    finally:
+        sys.path.remove("/root/reference")
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for k in [k for k in sys.modules if k.startswith("lib.pointnet2") or k == "lib"]:
+            sys.modules.pop(k, None)
