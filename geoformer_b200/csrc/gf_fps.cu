@@ -30,10 +30,50 @@ struct __align__(16) FpsSlot {
   float z;
   float pad[3];
 };
+static_assert(sizeof(FpsSlot) == 32, "slot is two 16-byte vectors");
 
 constexpr int FPS_MAX_CLUSTER = 16;
 
 __device__ __forceinline__ uint32_t brev_bits(uint32_t c, int L) { return L ? (__brev(c) >> (32 - L)) : 0u; }
+
+// ---- cluster-scope mbarrier signalling (replaces barrier.cluster in the round loop) -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// local arrival that also announces how many bytes of asynchronous stores this phase will receive
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 16-byte store into another CTA's shared memory that completes `16` transaction bytes on that CTA's
+// mbarrier when it lands: data and signal travel together, no fence on either side (a cluster-scope
+// acquire on the waiter would cost a CCTL.IVALL per round -- 46 % of the kernel in the first version).
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t remote_bar, uint32_t a, uint32_t b,
+                                            uint32_t c, uint32_t d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   remote_addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
 
 // P > 0 : register-resident variant, thread owns points k = c + bs*(g*P + i), i < P
 // P == 0: streaming variant for scenes that do not fit on chip: thread walks k = c + bs*(g + G*i)
@@ -50,7 +90,8 @@ __global__ void __launch_bounds__(T, 1)
   int *__restrict__ idx = idx_all + (size_t)scene * m;
 
   __shared__ FpsSlot slots[2][FPS_MAX_CLUSTER];
-  __shared__ uint32_t wkey_v[32], wkey_lo[32];
+  __shared__ uint32_t wkey_v[2][32], wkey_lo[2][32];  // by round parity: no CTA barrier closes a round
+  __shared__ __align__(8) uint64_t round_bar[2];  // by round parity: CS x 32 transaction bytes per phase
 
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned u = crank * T + tid;  // thread id inside the cluster
@@ -60,20 +101,22 @@ __global__ void __launch_bounds__(T, 1)
   const uint32_t rank_hi = L ? (brev_bits(c, L) << (32 - L)) : 0u;
 
   constexpr int PR = P > 0 ? P : 1;
+  // Points that can never be selected (padding, or |p|^2 <= 1e-3: sampling_gpu.cu:103-104) carry the
+  // sentinel running minimum -1: fminf(d, -1) stays -1 and never beats `best`, which starts at -1
+  // (the reference's initial value, :93) -- no per-point predicate in the round loop.
   float px[PR], py[PR], pz[PR], tmp[PR];
-  uint32_t elig = 0;
   if (P > 0) {
 #pragma unroll
     for (int i = 0; i < PR; ++i) {
       unsigned k = c + bs * (g * PR + i);
       px[i] = py[i] = pz[i] = 0.f;
-      tmp[i] = 1e10f;  // sampling.cpp:74-76
+      tmp[i] = -1.f;
       if (k < (unsigned)N) {
         px[i] = __ldg(xyz + (size_t)k * 3 + 0);
         py[i] = __ldg(xyz + (size_t)k * 3 + 1);
         pz[i] = __ldg(xyz + (size_t)k * 3 + 2);
         float mag = sq3(px[i], py[i], pz[i]);
-        if (!((double)mag <= 1e-3)) elig |= 1u << i;  // sampling_gpu.cu:103-104
+        if (!((double)mag <= 1e-3)) tmp[i] = 1e10f;  // eligible: sampling.cpp:74-76
       }
     }
   }
@@ -86,7 +129,12 @@ __global__ void __launch_bounds__(T, 1)
   int old = 0;
   float cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);
   if (u == 0) idx[0] = 0;
-  cluster.sync();  // temp initialised (streaming variant), slots not yet in use
+  if (tid == 0) {
+    mbar_init(&round_bar[0], 1);
+    mbar_init(&round_bar[1], 1);
+    mbar_fence_init();
+  }
+  cluster.sync();  // barriers initialised everywhere; temp initialised (streaming variant)
 
   for (int j = 1; j < m; ++j) {
     float best = -1.f;
@@ -95,14 +143,12 @@ __global__ void __launch_bounds__(T, 1)
     if (P > 0) {
 #pragma unroll
       for (int i = 0; i < PR; ++i) {
-        if (elig & (1u << i)) {
-          float d = sq3(px[i] - cx, py[i] - cy, pz[i] - cz);
-          float t = fminf(d, tmp[i]);
-          tmp[i] = t;
-          if (t > best) {
-            best = t;
-            besti = i;
-          }
+        float d = sq3(px[i] - cx, py[i] - cy, pz[i] - cz);
+        float t = fminf(d, tmp[i]);
+        tmp[i] = t;
+        if (t > best) {
+          best = t;
+          besti = i;
         }
       }
     } else {
@@ -130,32 +176,43 @@ __global__ void __launch_bounds__(T, 1)
     uint32_t wv = __reduce_max_sync(0xffffffffu, vb);
     uint32_t wl = __reduce_max_sync(0xffffffffu, vb == wv ? lo : 0u);
     if (lane == 0) {
-      wkey_v[warp] = wv;
-      wkey_lo[warp] = wl;
+      wkey_v[j & 1][warp] = wv;
+      wkey_lo[j & 1][warp] = wl;
     }
+    // this CTA's own arrival for the round (posted before its candidate can leave, i.e. before any
+    // other CTA can run ahead into the next use of this barrier)
+    if (tid == 0) mbar_arrive_expect_tx(&round_bar[j & 1], CS * (uint32_t)sizeof(FpsSlot));
     __syncthreads();
-    uint32_t tv = lane < T / 32 ? wkey_v[lane] : 0u;
-    uint32_t tl = lane < T / 32 ? wkey_lo[lane] : 0u;
+    uint32_t tv = lane < T / 32 ? wkey_v[j & 1][lane] : 0u;
+    uint32_t tl = lane < T / 32 ? wkey_lo[j & 1][lane] : 0u;
     const uint32_t cv = __reduce_max_sync(0xffffffffu, tv);
     const uint32_t cl = __reduce_max_sync(0xffffffffu, tv == cv ? tl : 0u);
 
     const int buf = j & 1;
     const bool owner = has && vb == cv && lo == cl;
     const bool nobody = (cv | cl) == 0u;
-    if (owner || (nobody && tid == 0)) {
+    // The warp that holds the CTA winner (warp 0 when the CTA has no eligible point) pushes the
+    // candidate into every CTA of the cluster: lane r stores it into CTA r's slot with st.async, which
+    // completes the transaction bytes of CTA r's round barrier when the data has landed.
+    const unsigned own_mask = __ballot_sync(0xffffffffu, owner);
+    if (own_mask || (nobody && warp == 0)) {
+      const int src = own_mask ? __ffs(own_mask) - 1 : 0;
       if (P > 0 && owner) {
 #pragma unroll
         for (int i = 0; i < PR; ++i)
           if (besti == (uint32_t)i) bx = px[i], by = py[i], bz = pz[i];
       }
-      FpsSlot s;
-      s.v = cv, s.lo = cl, s.x = bx, s.y = by, s.z = bz, s.pad[0] = s.pad[1] = s.pad[2] = 0.f;
-      for (unsigned r = 0; r < CS; ++r) {
-        FpsSlot *dst = cluster.map_shared_rank(&slots[buf][crank], r);
-        *dst = s;
+      const float sx = __shfl_sync(0xffffffffu, bx, src), sy = __shfl_sync(0xffffffffu, by, src),
+                  sz = __shfl_sync(0xffffffffu, bz, src);
+      if (lane < CS) {
+        const uint32_t dst = map_to_cta(smem_u32(&slots[buf][crank]), lane);
+        const uint32_t rbar = map_to_cta(smem_u32(&round_bar[buf]), lane);
+        st_async_v4(dst, rbar, cv, cl, __float_as_uint(sx), __float_as_uint(sy));
+        st_async_v4(dst + 16, rbar, __float_as_uint(sz), 0u, 0u, 0u);
       }
     }
-    cluster.sync();  // release/acquire: every CTA's candidate is visible in every CTA
+    // round j is use number (j-1)/2 of barrier j&1 (rounds start at 1): wait for that phase
+    mbar_wait(&round_bar[buf], (uint32_t)(((j - 1) >> 1) & 1));  // all CS candidates have landed in slots[buf]
 
     // lane r looks at CTA r's candidate; two REDUX steps pick the cluster-wide winner
     uint32_t sv = 0, sl = 0;
@@ -192,17 +249,19 @@ struct FpsPlan {
   int T, P, CS;
 };
 
+// Few, fat warps: a round costs (points per SM) x ~10 instructions of arithmetic plus ~150 instructions
+// of reduction / signalling PER WARP, so 8 warps with up to 32 register-resident points per thread beat
+// 32 warps with 8 (measured: 1.87 us -> see profiles/).  Capacity = CS * T * P.
+static const int kFpsP256[] = {1, 2, 4, 8, 12, 16, 20, 25, 32};
+
 static FpsPlan plan_fps(int N, int max_cs) {
-  // capacity = CS*T*P (in whole residue-class runs); prefer small clusters, then small P
-  const int cs_opts[5] = {1, 2, 4, 8, 16};
-  const int p_opts[4] = {1, 2, 4, 8};
-  for (int ci = 0; ci < 5; ++ci) {
-    int cs = cs_opts[ci];
-    if (cs > max_cs) break;
-    if ((long long)cs * 1024 * 8 < N) continue;
-    for (int pi = 0; pi < 4; ++pi)
-      if ((long long)cs * 1024 * p_opts[pi] >= N) return {1024, p_opts[pi], cs};
-  }
+  if (N < 512) return {256, N <= 256 ? 1 : 2, 1};  // reference block size bs <= 256 <= T
+  // smallest power-of-two cluster (>= 2 so that CS * 256 covers the 512 residue classes) whose
+  // 256-thread CTAs hold the scene with P <= 32; prefer the largest cluster (least work per SM per round)
+  int cs = max_cs;
+  while (cs > 2 && (long long)(cs / 2) * 256 * 4 >= N) cs /= 2;  // tiny scenes: do not spread thinner than 4 pts/thread
+  for (int pi = 0; pi < (int)(sizeof(kFpsP256) / sizeof(int)); ++pi)
+    if ((long long)cs * 256 * kFpsP256[pi] >= N) return {256, kFpsP256[pi], cs};
   if ((long long)max_cs * 512 * 24 >= N) return {512, 24, max_cs};
   return {1024, 0, max_cs};
 }
@@ -232,7 +291,7 @@ static int max_cluster_size() {
   // 16 (non-portable) when the device can co-schedule a 16-CTA x 1024-thread cluster, else 8
   static int cached = 0;
   if (cached) return cached;
-  auto kern = fps_cluster_kernel<1024, 8>;
+  auto kern = fps_cluster_kernel<1024, 0>;
   int ok16 = 0;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
@@ -289,10 +348,15 @@ extern "C" int gf_furthest_point_sampling(const float *xyz, int B, int N, int m,
   }
 #define GF_FPS_CASE(TT, PP) \
   if (p.T == TT && p.P == PP) return launch_fps<TT, PP>(xyz, B, N, m, L, p.CS, temp, idx, st)
-  GF_FPS_CASE(1024, 1);
-  GF_FPS_CASE(1024, 2);
-  GF_FPS_CASE(1024, 4);
-  GF_FPS_CASE(1024, 8);
+  GF_FPS_CASE(256, 1);
+  GF_FPS_CASE(256, 2);
+  GF_FPS_CASE(256, 4);
+  GF_FPS_CASE(256, 8);
+  GF_FPS_CASE(256, 12);
+  GF_FPS_CASE(256, 16);
+  GF_FPS_CASE(256, 20);
+  GF_FPS_CASE(256, 25);
+  GF_FPS_CASE(256, 32);
   GF_FPS_CASE(512, 24);
   GF_FPS_CASE(1024, 0);
 #undef GF_FPS_CASE
