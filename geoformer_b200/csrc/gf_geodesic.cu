@@ -11,45 +11,48 @@
 // Formulation.  The Q seeds are independent BFS runs over the same graph, so ONE CTA owns ONE seed
 // from its first level to its last (persistent CTAs pull seeds from a counter).  Level
 // synchronisation is a __syncthreads() -- no grid barrier, no host round trip (the reference
-// synchronises the host >= 3 times per level) -- and the state of a run lives in shared memory:
-//   * visited set: a bitmap (N bits);
-//   * frontier: a compacted queue of (point, distance) pairs;
-//   * claims: an open-addressing hash table  target -> min over candidates of
-//         (parent index << SB | slot) << 32 | bits(distance candidate)
-//     filled with 64-bit atomicMin.  The 32 high bits order candidates exactly like the reference's
-//     tie rule; the low bits carry the winner's distance D[p][j] + dist(p) (one fp32 add, as the
-//     reference), so after the CTA barrier every table entry IS a finished (point, distance) pair:
-//     it is written to the output row, marked visited and appended to the next frontier.
-// The only global access on a level's critical path is the load of the frontier points' edge rows.
-// The graph is first packed (one small kernel per scene) into 8-byte (target, length) entries, K
-// padded to a power of two, with the radius / validity filter (:123, :151) already applied, so a
-// frontier point costs one aligned 128-byte load when k = 16.
-// Levels whose frontier or claim set does not fit on chip take a slower exact path that claims
-// through the output row itself (atomicMin of the key, distances resolved after the barrier).
+// synchronises the host >= 3 times per level).  Per seed, in shared memory: the visited bitmap, a
+// "claimed at this level" bitmap and the compacted frontier queue (point ids).  The seed's own output
+// row geo[q][:] doubles as the claim array:
+//   pass A  a group of KP lanes expands one frontier point p (lane = neighbour slot j, one aligned
+//           128-byte load of packed {target, length} edges at k = 16).  An edge to an unvisited t claims
+//           it with a fire-and-forget  RED.MIN(bits(geo[q][t]), 0x80000000 | p << SB | j):  smaller than
+//           "unvisited" (-1.0f = 0xBF800000), larger than any finished distance (a non-negative float),
+//           and ordered exactly like the reference's tie rule (parent index, then slot).  A test-and-set
+//           on the claimed bitmap (shared-memory atomic, ~100 cycles) tells the first claimant of t, which
+//           appends t to the next frontier -- no atomic return value is ever waited for.
+//   pass B  (after the CTA barrier) for every new point the key left in its row entry IS the reference's
+//           winner: decode (p, j), read the edge length and p's finished distance, write
+//           geo[q][t] = D[p][j] + geo[q][p] (one fp32 add, as the reference), move the claimed bit to the
+//           visited bitmap.
+// The inner loop has no bounds or validity branches: frontier queues are padded with the sentinel point N,
+// whose edge row holds only edges to N, and bit N of the visited bitmap is always set, so padding and
+// filtered edges (radius / missing neighbour, :123 / :151, applied once when the graph is packed) look
+// like edges to an already visited point.  ~20 instructions per edge instead of ~120 for the earlier
+// hash-table formulation (both measured).
+// Levels whose frontier does not fit the on-chip queue read its tail from a global overflow area;
+// scenes too large for the two bitmaps (N > ~800k) test / claim through the row with returning atomics.
 #include <stdlib.h>
 
 #include "gf_geodesic.cuh"
 
 namespace gf {
 
-constexpr int GEO_THREADS = 512;
-constexpr int GEO_QCAP = 2048;  // frontier entries kept in shared memory (per buffer)
-constexpr int GEO_HBITS = 12;
-constexpr int GEO_HCAP = 1 << GEO_HBITS;  // claim hash table slots
-constexpr int GEO_HPROBE = 64;            // probe limit before a level is declared "does not fit"
-constexpr int GEO_UNROLL = 8;
+constexpr int GEO_THREADS = 1024;
+constexpr int GEO_QCAP = 4096;  // frontier entries kept in shared memory (per buffer)
+constexpr int GEO_UNROLL = 4;
 constexpr uint32_t GEO_UNVISITED = 0xBF800000u;  // bits of -1.0f
 constexpr uint32_t GEO_KEYBIT = 0x80000000u;
 constexpr uint32_t GEO_KEYMAX = 0x3F800000u;  // row-claim keys must stay below "unvisited"
 constexpr int GEO_EMPTY = -1;
 
 struct GeoArgs {
-  const int2 *edges;  // (N, KP) packed {target or -1, length bits}
+  const int2 *edges;  // (N + 1, KP) packed {target, length bits}; unusable edges and row N point to N
   int N, Q, max_step;
   int slot_bits;  // KP = 1 << slot_bits
   const int *seeds;
   float *geo;                 // (Q,N)
-  int2 *overflow;             // per CTA: N + 2 frontier entries beyond GEO_QCAP (two stacks, one per end)
+  int *overflow;              // per CTA: N + 2 frontier entries beyond GEO_QCAP (two stacks, one per end)
   unsigned *seed_counter;     // work distribution
   unsigned long long *stats;  // [0] reached pairs, [1] deepest level (atomicMax)
   int bitmap_words;           // shared-memory visited bitmap size (0 = test the output row instead)
@@ -66,17 +69,18 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
 
 // ---- edge packing ---------------------------------------------------------------------------------
 // edges[p][j] = {I[p][1+j], D[p][1+j]} if the edge may ever be used (D <= radius, 0 <= I < N;
-// geodesic_utils.py:123,151), else {-1, 0}; column 0 of the kNN result is dropped (:110-111).
+// geodesic_utils.py:123,151), else {N, 0}; column 0 of the kNN result is dropped (:110-111).
+// Row N (the sentinel point used to pad frontier queues) has only edges to N.
 template <bool IS64>
 __global__ void geo_pack_edges_kernel(const float *__restrict__ D, const void *__restrict__ I, int N, int k,
                                       float radius, int slot_bits, int2 *__restrict__ edges) {
   const int KP = 1 << slot_bits, K = k - 1;
-  const long long total = (long long)N << slot_bits;
+  const long long total = ((long long)N + 1) << slot_bits;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(e >> slot_bits), j = (int)(e & (KP - 1));
-    int2 out = make_int2(GEO_EMPTY, 0);
-    if (j < K) {
+    int2 out = make_int2(N, 0);
+    if (j < K && p < N) {
       const size_t at = (size_t)p * k + 1 + j;
       const long long t = IS64 ? ((const long long *)I)[at] : (long long)((const int *)I)[at];
       const float w = __ldg(D + at);
@@ -94,165 +98,48 @@ __device__ __forceinline__ size_t ovf_index(int i, int level_parity, int N) {
   const size_t j = (size_t)(i - GEO_QCAP);
   return level_parity ? j : (size_t)N + 1 - j;
 }
-__device__ __forceinline__ int2 frontier_get(const int2 *sq, const int2 *ovf, int i, int level_parity, int N) {
-  return i < GEO_QCAP ? sq[i] : ovf[ovf_index(i, level_parity, N)];
-}
-__device__ __forceinline__ void frontier_put(int2 *sq, int2 *ovf, int i, int level_parity, int N, int2 e) {
+__device__ __forceinline__ void frontier_put(int *sq, int *ovf, int i, int level_parity, int N, int t) {
   if (i < GEO_QCAP)
-    sq[i] = e;
+    sq[i] = t;
   else
-    ovf[ovf_index(i, level_parity, N)] = e;
+    ovf[ovf_index(i, level_parity, N)] = t;
 }
 
-struct GeoSmem {
-  int2 *q0, *q1;
-  int *tag;
-  unsigned long long *val;
-  uint32_t *vis;
-};
-
-// ---- one level, on-chip path (frontier <= GEO_QCAP) --------------------------------------------------
-// Returns false (block-uniform) when the claim table overflowed; nothing global has been touched then.
+// one candidate edge p --(slot)--> t of the current level (t == N for padding / unusable edges)
 template <bool BITMAP>
-__device__ __forceinline__ bool geo_level_hash(const GeoArgs &a, const GeoSmem &sm, int level, int F, const int2 *fq,
-                                               int2 *nq, int2 *ovf, float *row, int *s_next_n, int *s_flag) {
-  const uint32_t *rowu = reinterpret_cast<const uint32_t *>(row);
-  const int N = a.N;
-  const unsigned sb = (unsigned)a.slot_bits, KP = 1u << sb;
-  const unsigned tid = threadIdx.x;
-  const unsigned slot = tid & (KP - 1), group = tid >> sb, ngroups = GEO_THREADS >> sb;
-  // ---- pass A: a group of KP lanes expands one frontier point (lane = neighbour slot) ---------------
-  for (int n0 = (int)group; n0 < F; n0 += (int)ngroups * GEO_UNROLL) {
-    int2 pe[GEO_UNROLL], ed[GEO_UNROLL];
-#pragma unroll
-    for (int u = 0; u < GEO_UNROLL; ++u) {
-      const int node = n0 + u * (int)ngroups;
-      pe[u] = node < F ? fq[node] : make_int2(GEO_EMPTY, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < GEO_UNROLL; ++u)
-      ed[u] = pe[u].x >= 0 ? __ldg(a.edges + (((size_t)pe[u].x) << sb) + slot) : make_int2(GEO_EMPTY, 0);
-#pragma unroll
-    for (int u = 0; u < GEO_UNROLL; ++u) {
-      const int t = ed[u].x;
-      if (t < 0) continue;
-      const bool seen = BITMAP ? (sm.vis[(unsigned)t >> 5] >> (t & 31)) & 1u : ld_cg_u32(rowu + t) < GEO_KEYBIT;
-      if (seen) continue;
-      // level 1: the distance is the edge itself (:127); later: edge + parent's distance (:144)
-      const float d =
-          level == 1 ? __int_as_float(ed[u].y) : __fadd_rn(__int_as_float(ed[u].y), __int_as_float(pe[u].y));
-      const unsigned long long v =
-          ((unsigned long long)(((unsigned)pe[u].x << sb) | slot) << 32) | (unsigned)__float_as_int(d);
-      unsigned h = ((unsigned)t * 2654435761u) >> (32 - GEO_HBITS);
-      int probes = 0;
-      for (;;) {
-        const int old = atomicCAS(sm.tag + h, GEO_EMPTY, t);
-        if (old == GEO_EMPTY || old == t) {
-          atomicMin(sm.val + h, v);
-          break;
-        }
-        h = (h + 1) & (GEO_HCAP - 1);
-        if (++probes >= GEO_HPROBE) {
-          *s_flag = 1;
-          break;
-        }
-      }
-    }
+__device__ __forceinline__ void geo_claim(int p, int t, unsigned slot, unsigned sb, int N, int level, uint32_t *vis,
+                                          uint32_t *clm, uint32_t *rowu, int *nq, int *ovf, int *s_next_n) {
+  const uint32_t key = GEO_KEYBIT | ((uint32_t)p << sb) | slot;
+  if (BITMAP) {
+    const unsigned tw = (unsigned)t >> 5, tb = 1u << (t & 31);
+    if (vis[tw] & tb) return;             // visited, padding, or filtered edge
+    atomicMin(rowu + t, key);             // RED.MIN: fire and forget
+    if (atomicOr(clm + tw, tb) & tb) return;  // somebody claimed t earlier in this level
+  } else {
+    if (t >= N || ld_cg_u32(rowu + t) < GEO_KEYBIT) return;
+    if (atomicMin(rowu + t, key) != GEO_UNVISITED) return;
   }
-  __syncthreads();
-  const bool failed = *s_flag != 0;
-  // ---- pass B: every table entry is a finished (point, distance) pair; clear the table ----------------
-  for (int h = tid; h < GEO_HCAP; h += GEO_THREADS) {
-    const int t = sm.tag[h];
-    if (t == GEO_EMPTY) continue;
-    const unsigned long long v = sm.val[h];
-    sm.tag[h] = GEO_EMPTY;
-    sm.val[h] = ~0ull;
-    if (failed) continue;
-    const int dbits = (int)(unsigned)(v & 0xffffffffu);
-    row[t] = __int_as_float(dbits);                                      // :139
-    if (BITMAP) atomicOr(sm.vis + ((unsigned)t >> 5), 1u << (t & 31));  // :140
-    const int pos = atomicAdd(s_next_n, 1);
-    frontier_put(nq, ovf, pos, level & 1, N, make_int2(t, dbits));
-  }
-  return !failed;
-}
-
-// ---- one level, general path (any frontier size) -------------------------------------------------------
-//   pass A  every valid candidate (parent p, slot j) -> t claims t with atomicMin of its key on the
-//           output row (unvisited = -1.0f = 0xBF800000 > any key > any finished distance); the claimant
-//           that finds the entry still "unvisited" appends t to the next frontier (once per new point).
-//   pass B  (after the barrier) the key left in the entry is the reference's winner: decode it, read the
-//           edge length and the parent's finished distance, write the distance, mark the point visited.
-template <bool BITMAP>
-__device__ __forceinline__ void geo_level_row(const GeoArgs &a, const GeoSmem &sm, int level, int F, const int2 *fq,
-                                              int2 *nq, int2 *ovf, float *row, int *s_next_n) {
-  uint32_t *rowu = reinterpret_cast<uint32_t *>(row);
-  const int N = a.N;
-  const unsigned sb = (unsigned)a.slot_bits, KP = 1u << sb;
-  const unsigned tid = threadIdx.x;
-  const int par = (level - 1) & 1;
-  const unsigned ncand = (unsigned)F << sb;  // < 2^30 by the host-side key check
-  for (unsigned c0 = tid; c0 < ncand; c0 += GEO_THREADS * 4) {
-    unsigned key[4];
-    int t[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const unsigned c = c0 + u * GEO_THREADS;
-      t[u] = GEO_EMPTY;
-      key[u] = 0u;
-      if (c < ncand) {
-        const int p = frontier_get(fq, ovf, (int)(c >> sb), par, N).x;
-        t[u] = __ldg(a.edges + (((size_t)p) << sb) + (c & (KP - 1))).x;
-        key[u] = GEO_KEYBIT | ((unsigned)p << sb) | (c & (KP - 1));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (t[u] < 0) continue;
-      const bool seen =
-          BITMAP ? (sm.vis[(unsigned)t[u] >> 5] >> (t[u] & 31)) & 1u : ld_cg_u32(rowu + t[u]) < GEO_KEYBIT;
-      if (seen) continue;
-      if (atomicMin(rowu + t[u], key[u]) == GEO_UNVISITED)  // first claimant of t at this level
-        frontier_put(nq, ovf, atomicAdd(s_next_n, 1), level & 1, N, make_int2(t[u], 0));
-    }
-  }
-  __syncthreads();
-  const int nextF = *s_next_n;
-  for (int i = tid; i < nextF; i += GEO_THREADS) {
-    int2 *entry = i < GEO_QCAP ? nq + i : ovf + ovf_index(i, level & 1, N);
-    const int t = entry->x;
-    const uint32_t key = ld_cg_u32(rowu + t);
-    const unsigned p = (key & 0x7fffffffu) >> sb, slot = key & (KP - 1);
-    const float w = __int_as_float(__ldg(a.edges + (((size_t)p) << sb) + slot).y);
-    const float d = level == 1 ? w : __fadd_rn(w, __uint_as_float(ld_cg_u32(rowu + p)));  // :127 / :144
-    row[t] = d;                                                                         // :139
-    if (BITMAP) atomicOr(sm.vis + ((unsigned)t >> 5), 1u << (t & 31));                 // :140
-    *entry = make_int2(t, __float_as_int(d));
-  }
+  frontier_put(nq, ovf, atomicAdd(s_next_n, 1), level & 1, N, t);  // first claimant: t joins the next frontier
 }
 
 template <bool BITMAP>
 __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GeoSmem sm;
-  sm.val = reinterpret_cast<unsigned long long *>(smem_raw);
-  sm.q0 = reinterpret_cast<int2 *>(sm.val + GEO_HCAP);
-  sm.q1 = sm.q0 + GEO_QCAP;
-  sm.tag = reinterpret_cast<int *>(sm.q1 + GEO_QCAP);
-  sm.vis = reinterpret_cast<uint32_t *>(sm.tag + GEO_HCAP);
-  __shared__ int s_next_n, s_seed_q, s_flag;
+  int *q0 = reinterpret_cast<int *>(smem_raw);
+  int *q1 = q0 + GEO_QCAP;
+  uint32_t *vis = reinterpret_cast<uint32_t *>(q1 + GEO_QCAP);
+  uint32_t *clm = vis + a.bitmap_words;
+  __shared__ int s_next_n, s_seed_q;
 
   const int N = a.N;
-  const int tid = threadIdx.x;
-  int2 *ovf = a.overflow + (size_t)blockIdx.x * ((size_t)N + 2);
+  const unsigned sb = (unsigned)a.slot_bits, KP = 1u << sb;
+  const unsigned tid = threadIdx.x;
+  const unsigned slot = tid & (KP - 1), group = tid >> sb, ngroups = GEO_THREADS >> sb;
+  const int2 *__restrict__ erow = a.edges + slot;  // + (p << sb): this lane's column of the edge rows
+  int *ovf = a.overflow + (size_t)blockIdx.x * ((size_t)N + 2);
   unsigned long long reached_total = 0;
   int deepest = 0;
 
-  for (int h = tid; h < GEO_HCAP; h += GEO_THREADS) {
-    sm.tag[h] = GEO_EMPTY;
-    sm.val[h] = ~0ull;
-  }
   for (;;) {
     if (tid == 0) s_seed_q = (int)atomicAdd(a.seed_counter, 1u);
     __syncthreads();
@@ -260,7 +147,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
     if (q >= a.Q) break;
     float *row = a.geo + (size_t)q * N;
     uint32_t *rowu = reinterpret_cast<uint32_t *>(row);
-    {  // init: row = -1 (geodesic_utils.py:113), visited = {} (:114)
+    {  // init: row = -1 (geodesic_utils.py:113), visited = claimed = {} (:114), sentinel bit N set
       const size_t head = ((16 - ((uintptr_t)row & 15)) & 15) / 4;
       const size_t h = head < (size_t)N ? head : (size_t)N;
       const size_t nvec = ((size_t)N - h) / 4;
@@ -271,62 +158,74 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
       const size_t tail0 = h + nvec * 4;
       if ((size_t)tid < (size_t)N - tail0) row[tail0 + tid] = -1.f;
       if (BITMAP)
-        for (int i = tid; i < a.bitmap_words; i += GEO_THREADS) sm.vis[i] = 0u;
+        for (int i = tid; i < 2 * a.bitmap_words; i += GEO_THREADS) vis[i] = 0u;  // vis and clm are contiguous
     }
     const int s = a.seeds[q];
     const bool seed_ok = s >= 0 && s < N;  // the reference would raise an index error; the row stays -1
+    __syncthreads();
     if (tid == 0) {
       s_next_n = 0;
-      s_flag = 0;
-      if (seed_ok) sm.q0[0] = make_int2(s, __float_as_int(0.f));  // :118, distance of the seed
+      if (BITMAP) vis[(unsigned)N >> 5] |= 1u << (N & 31);
     }
+    // frontier of level 1 = {seed}, padded with the sentinel point N
+    for (int i = tid; i < (int)ngroups * GEO_UNROLL; i += GEO_THREADS) q0[i] = (i == 0 && seed_ok) ? s : N;
     __syncthreads();
     int F = seed_ok ? 1 : 0;
-    int2 *fq = sm.q0, *nq = sm.q1;
+    int *fq = q0, *nq = q1;
     // NOTE the seed is NOT marked visited before level 1: the reference's first expansion has no
     // visited filter (:123), so a seed that appears in its own neighbour row is re-won at level 1.
     int level = 0;
     while (F > 0 && level < a.max_step) {
       ++level;
-#ifdef GF_TRACE
-      if (blockIdx.x == 0 && tid == 0 && level < 300) {
-        long long tnow;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tnow));
-        a.trace[level * 4 + 0] = tnow;
+      // ---- pass A: claims ---------------------------------------------------------------------------
+      const int Fs = F < GEO_QCAP ? F : GEO_QCAP;  // on-chip part (padded to whole batches with N)
+      for (int n0 = (int)group; n0 < Fs; n0 += (int)ngroups * GEO_UNROLL) {
+        int p[GEO_UNROLL];
+        int2 e[GEO_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GEO_UNROLL; ++u) p[u] = fq[n0 + u * (int)ngroups];
+#pragma unroll
+        for (int u = 0; u < GEO_UNROLL; ++u) e[u] = __ldg(erow + ((size_t)p[u] << sb));
+#pragma unroll
+        for (int u = 0; u < GEO_UNROLL; ++u) geo_claim<BITMAP>(p[u], e[u].x, slot, sb, N, level, vis, clm, rowu, nq, ovf, &s_next_n);
       }
-#endif
-      bool done = false;
-      if (F <= GEO_QCAP) {
-        done = geo_level_hash<BITMAP>(a, sm, level, F, fq, nq, ovf, row, &s_next_n, &s_flag);
-        if (!done) {  // claim table overflowed: it has been cleared, nothing else was touched
-          __syncthreads();
-          if (tid == 0) s_flag = 0;
+      for (int node = GEO_QCAP + (int)group; node < F; node += (int)ngroups) {  // spilled tail (rare)
+        const int p = ovf[ovf_index(node, (level - 1) & 1, N)];
+        geo_claim<BITMAP>(p, __ldg(erow + ((size_t)p << sb)).x, slot, sb, N, level, vis, clm, rowu, nq, ovf, &s_next_n);
+      }
+      __syncthreads();
+      // ---- pass B: the key left in the row entry of a new point is the reference's winner ------------
+      const int nextF = s_next_n;
+      for (int i = tid; i < nextF; i += GEO_THREADS) {
+        const int t = i < GEO_QCAP ? nq[i] : ovf[ovf_index(i, level & 1, N)];
+        const uint32_t key = ld_cg_u32(rowu + t);
+        const unsigned p = (key & 0x7fffffffu) >> sb, j = key & (KP - 1);
+        const float w = __int_as_float(__ldg(a.edges + ((size_t)p << sb) + j).y);
+        // level 1: the distance is the edge itself (:127); later: edge + parent's distance (:144)
+        row[t] = level == 1 ? w : __fadd_rn(w, __uint_as_float(ld_cg_u32(rowu + p)));  // :139
+        if (BITMAP) {                                                                    // :140
+          atomicOr(vis + ((unsigned)t >> 5), 1u << (t & 31));
+          atomicAnd(clm + ((unsigned)t >> 5), ~(1u << (t & 31)));
         }
       }
-      if (!done) geo_level_row<BITMAP>(a, sm, level, F, fq, nq, ovf, row, &s_next_n);
-      __syncthreads();
-      const int nextF = s_next_n;
-#ifdef GF_TRACE
-      if (blockIdx.x == 0 && tid == 0 && level < 300) {
-        long long tnow;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tnow));
-        a.trace[level * 4 + 1] = tnow;
-        a.trace[level * 4 + 3] = ((long long)F << 32) | (unsigned)nextF;
+      // pad the new frontier to whole batches with the sentinel
+      {
+        const int padded = ((nextF + (int)ngroups * GEO_UNROLL - 1) / ((int)ngroups * GEO_UNROLL)) * ((int)ngroups * GEO_UNROLL);
+        for (int i = nextF + (int)tid; i < padded && i < GEO_QCAP; i += GEO_THREADS) nq[i] = N;
       }
-#endif
       __syncthreads();
       if (tid == 0) {
         s_next_n = 0;
         if (level == 1) {
           // the seed joins the visited set now; if no self edge re-won it, its distance stays 0
           if (ld_cg_u32(rowu + s) == GEO_UNVISITED) row[s] = 0.f;
-          if (BITMAP) sm.vis[s >> 5] |= 1u << (s & 31);
+          if (BITMAP) vis[(unsigned)s >> 5] |= 1u << (s & 31);
         }
       }
       if (nextF > 0) deepest = level > deepest ? level : deepest;
       reached_total += (unsigned long long)nextF;
       F = nextF;
-      int2 *tq = fq;
+      int *tq = fq;
       fq = nq;
       nq = tq;
       __syncthreads();
@@ -352,21 +251,21 @@ struct GeoPlan {
 
 // shared-memory plan, identical for sizing and launching: 227 KB usable per CTA and per SM on sm_100
 static void geo_smem_plan(int N, int *bitmap_words, size_t *smem, int *ctas_per_sm) {
-  const size_t fixed = sizeof(int2) * 2 * GEO_QCAP + (sizeof(int) + sizeof(unsigned long long)) * GEO_HCAP;
-  int words = (N + 31) / 32;
-  size_t bytes = fixed + sizeof(uint32_t) * (size_t)words;
+  const size_t fixed = sizeof(int) * 2 * GEO_QCAP;
+  int words = (N + 1 + 31) / 32;  // + the sentinel point N
+  size_t bytes = fixed + sizeof(uint32_t) * 2 * (size_t)words;
   static int no_bitmap = -1;
   if (no_bitmap < 0) {
     const char *e = getenv("GF_GEO_NOBITMAP");  // test knob: force the large-scene variant
     no_bitmap = e ? atoi(e) : 0;
   }
-  if (no_bitmap || bytes > (size_t)226 * 1024) {  // no on-chip bitmap: test the output row instead
+  if (no_bitmap || bytes > (size_t)226 * 1024) {  // no on-chip bitmaps: test / claim through the row
     words = 0;
     bytes = fixed;
   }
   int per_sm = (int)((size_t)(227 * 1024) / (bytes + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2) per_sm = 2;  // __launch_bounds__(512, 2)
+  if (per_sm > 2) per_sm = 2;  // __launch_bounds__(GEO_THREADS, 2)
   *bitmap_words = words;
   *smem = bytes;
   *ctas_per_sm = per_sm;
@@ -396,8 +295,8 @@ size_t geodesic_workspace_bytes(int N, int k, int Q) {
   if (grid < 1) grid = 1;
   const int sb = ceil_log2(k - 1 > 1 ? k - 1 : 1);
   size_t b = 0;
-  b += align256(sizeof(int2) * ((size_t)N << sb));               // packed edges
-  b += align256(sizeof(int2) * ((size_t)N + 2) * (size_t)grid);  // frontier overflow
+  b += align256(sizeof(int2) * (((size_t)N + 1) << sb));        // packed edges (+ sentinel row)
+  b += align256(sizeof(int) * ((size_t)N + 2) * (size_t)grid);  // frontier overflow
   b += align256(64);                                             // seed counter
   b += align256(64);                                             // stats
   return b + 1024;
@@ -411,13 +310,13 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
   int rc = plan_geo(N, Q, &p);
   if (rc) return rc;
   const int slot_bits = ceil_log2(K > 1 ? K : 1);
-  if (((unsigned long long)N << slot_bits) >= GEO_KEYMAX) {
+  if ((((unsigned long long)N + 1) << slot_bits) >= GEO_KEYMAX) {
     set_error("geodesic: N=%d with k=%d does not fit the 30-bit claim key (N << %d must be < 2^30)", N, k, slot_bits);
     return GF_ERR_INVALID;
   }
   Arena a(workspace, workspace_bytes);
-  int2 *edges = a.take<int2>((size_t)N << slot_bits);
-  int2 *overflow = a.take<int2>(((size_t)N + 2) * (size_t)p.grid);
+  int2 *edges = a.take<int2>(((size_t)N + 1) << slot_bits);
+  int *overflow = a.take<int>(((size_t)N + 2) * (size_t)p.grid);
   unsigned *counter = a.take<unsigned>(16);
   unsigned long long *stats = a.take<unsigned long long>(8);
   if (!a.ok) {
@@ -428,7 +327,7 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
   GF_CUDA(cudaMemsetAsync(counter, 0, 64, st));
   GF_CUDA(cudaMemsetAsync(stats, 0, 64, st));
   {
-    const long long total = (long long)N << slot_bits;
+    const long long total = ((long long)N + 1) << slot_bits;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     const int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
