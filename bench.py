@@ -37,6 +37,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
     ap.add_argument("--max-step", type=int, default=None, help="override the workload's level bound")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="scenes in flight on the device (CUDA streams alternated step by step); 1 = strictly serial")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -277,10 +279,22 @@ def run_ours(args):
     sampler.start()
     C.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # consecutive steps alternate between `--streams` CUDA streams so that the latency-bound FPS of scene
+    # i+1 (one 16-SM cluster) overlaps the propagation of scene i; every step still runs the whole hot path
+    nstreams = max(1, min(args.streams, S))
+    side = [torch.cuda.Stream(device=dev) for _ in range(nstreams)] if nstreams > 1 else [stream]
     e0.record(stream)
+    for st_ in side:
+        if st_ is not stream:
+            st_.wait_event(e0)
     for i in range(K):
         L.gf_set_stage_events(ev_arr[i], 5)
-        runners[i % S].run(xs[i % S], stream)
+        runners[i % S].run(xs[i % S], side[i % nstreams])
+    for st_ in side:
+        if st_ is not stream:
+            done = torch.cuda.Event()
+            done.record(st_)
+            stream.wait_event(done)
     e1.record(stream)
     barrier()
     launches = C.launch_count()
@@ -366,7 +380,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_block(cfg, args, extra={
                 "parallelism": "scene-parallel x%d (one scene per rank per step, no collective)" % world,
-                "l2": "%d rotating scenes per rank, %.0f MB footprint each (> 126 MB L2 in total)" % (S, per_scene / 1e6)}),
+                "l2": "%d rotating scenes per rank, %.0f MB footprint each (> 126 MB L2 in total)" % (S, per_scene / 1e6),
+                "streams": nstreams}),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stage_ms": stage_ms, "scenes_per_s": value / Q,
         }

@@ -106,10 +106,10 @@ __device__ __forceinline__ void frontier_put(int *sq, int *ovf, int i, int level
 }
 
 // one candidate edge p --(slot)--> t of the current level (t == N for padding / unusable edges)
+// key = 0x80000000 | p << SB | slot, passed in pre-assembled (the shift is shared with the row address)
 template <bool BITMAP>
-__device__ __forceinline__ void geo_claim(int p, int t, unsigned slot, unsigned sb, int N, int level, uint32_t *vis,
-                                          uint32_t *clm, uint32_t *rowu, int *nq, int *ovf, int *s_next_n) {
-  const uint32_t key = GEO_KEYBIT | ((uint32_t)p << sb) | slot;
+__device__ __forceinline__ void geo_claim(uint32_t key, int t, int N, int level, uint32_t *vis, uint32_t *clm,
+                                          uint32_t *rowu, int *nq, int *ovf, int *s_next_n) {
   if (BITMAP) {
     const unsigned tw = (unsigned)t >> 5, tb = 1u << (t & 31);
     if (vis[tw] & tb) return;             // visited, padding, or filtered edge
@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
   const unsigned tid = threadIdx.x;
   const unsigned slot = tid & (KP - 1), group = tid >> sb, ngroups = GEO_THREADS >> sb;
   const int2 *__restrict__ erow = a.edges + slot;  // + (p << sb): this lane's column of the edge rows
+  const uint32_t keybase = GEO_KEYBIT | slot;
   int *ovf = a.overflow + (size_t)blockIdx.x * ((size_t)N + 2);
   unsigned long long reached_total = 0;
   int deepest = 0;
@@ -180,18 +181,19 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
       // ---- pass A: claims ---------------------------------------------------------------------------
       const int Fs = F < GEO_QCAP ? F : GEO_QCAP;  // on-chip part (padded to whole batches with N)
       for (int n0 = (int)group; n0 < Fs; n0 += (int)ngroups * GEO_UNROLL) {
-        int p[GEO_UNROLL];
-        int2 e[GEO_UNROLL];
+        unsigned ps[GEO_UNROLL];  // p << sb: 32-bit, (N + 1) << sb < 2^30 by the host-side key check
+        int t[GEO_UNROLL];
 #pragma unroll
-        for (int u = 0; u < GEO_UNROLL; ++u) p[u] = fq[n0 + u * (int)ngroups];
+        for (int u = 0; u < GEO_UNROLL; ++u) ps[u] = (unsigned)fq[n0 + u * (int)ngroups] << sb;
 #pragma unroll
-        for (int u = 0; u < GEO_UNROLL; ++u) e[u] = __ldg(erow + ((size_t)p[u] << sb));
+        for (int u = 0; u < GEO_UNROLL; ++u) t[u] = __ldg(&erow[ps[u]].x);
 #pragma unroll
-        for (int u = 0; u < GEO_UNROLL; ++u) geo_claim<BITMAP>(p[u], e[u].x, slot, sb, N, level, vis, clm, rowu, nq, ovf, &s_next_n);
+        for (int u = 0; u < GEO_UNROLL; ++u)
+          geo_claim<BITMAP>(keybase | ps[u], t[u], N, level, vis, clm, rowu, nq, ovf, &s_next_n);
       }
       for (int node = GEO_QCAP + (int)group; node < F; node += (int)ngroups) {  // spilled tail (rare)
-        const int p = ovf[ovf_index(node, (level - 1) & 1, N)];
-        geo_claim<BITMAP>(p, __ldg(erow + ((size_t)p << sb)).x, slot, sb, N, level, vis, clm, rowu, nq, ovf, &s_next_n);
+        const unsigned ps = (unsigned)ovf[ovf_index(node, (level - 1) & 1, N)] << sb;
+        geo_claim<BITMAP>(keybase | ps, __ldg(&erow[ps].x), N, level, vis, clm, rowu, nq, ovf, &s_next_n);
       }
       __syncthreads();
       // ---- pass B: the key left in the row entry of a new point is the reference's winner ------------
