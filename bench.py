@@ -10,8 +10,9 @@ scene of the workload (default c2: 100k points, 256 seeds, k=16, radius 0.5, 32 
   value     whole-job maps/s with the scenes already resident in HBM (CUDA events, max over ranks)
   e2e       the same through the host-buffer C-ABI call gf_guidance_host: pinned host points in,
             seeds + maps back in pinned host memory, copies inside the timed region
-  roofline  the level kernel (geo_levels_kernel): algorithmic bytes of SURVEY 8(d) / its live
-            CUDA-event duration, against the measured HBM peak (MEASURED_PEAKS.json)
+  roofline  the propagation kernel (geo_seed_bfs_kernel): algorithmic bytes of SURVEY 8(d) / its live
+            CUDA-event duration in the timed region, against the measured HBM peak (MEASURED_PEAKS.json);
+            `*_alone` = the same kernel timed in a short serial pass (one scene in flight)
   cpu_baseline  the CPU oracle port (oracle/) on this box's host cores, bounded sample (N=1 only)
 --impl reference times that CPU port as the reference arm (the reference's own torch code cannot
 travel to the GPU box and its kNN is faiss-gpu, absent everywhere).
@@ -32,12 +33,12 @@ sys.path.insert(0, ROOT)
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
     ap.add_argument("--max-step", type=int, default=None, help="override the workload's level bound")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=4,
                     help="scenes in flight on the device (CUDA streams alternated step by step); 1 = strictly serial")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -84,7 +85,7 @@ def ncu_traffic():
 class ClockSampler(threading.Thread):
     """samples SM clock and throttle reasons of one GPU through NVML while the timed region runs"""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -312,9 +313,31 @@ def run_ours(args):
         v = [x for x in v if x >= 0]
         return statistics.mean(v) if v else None
 
-    stage_ms = {"knn_grid_build": stage(0, 1), "knn_query_and_fps_join": stage(1, 2), "geodesic_csr_and_fill": stage(2, 3),
-                "geodesic_levels": stage(3, 4), "whole_call": stage(0, 4)}
+    stage_ms = {"knn_grid_build": stage(0, 1), "knn_query_and_fps_join": stage(1, 2), "geodesic_pack_edges": stage(2, 3),
+                "geodesic_propagation": stage(3, 4), "whole_call": stage(0, 4)}
     for e in ev:
+        for h in e:
+            L.gf_event_destroy(h)
+
+    # ---- short serial pass (one scene in flight): per-stage times without inter-scene overlap ----------
+    Ks = 12
+    ev_s = [[L.gf_event_create() for _ in range(5)] for _ in range(Ks)]
+    arr_s = [(ctypes.c_void_p * 5)(*e) for e in ev_s]
+    torch.cuda.synchronize(dev)
+    for i in range(Ks):
+        L.gf_set_stage_events(arr_s[i], 5)
+        runners[i % S].run(xs[i % S], stream)
+    torch.cuda.synchronize(dev)
+
+    def stage_serial(a, b):
+        v = [L.gf_event_elapsed_ms(e[a], e[b]) for e in ev_s[2:]]
+        v = [x for x in v if x >= 0]
+        return statistics.mean(v) if v else None
+
+    stage_ms_serial = {"knn_grid_build": stage_serial(0, 1), "knn_query_and_fps_join": stage_serial(1, 2),
+                       "geodesic_pack_edges": stage_serial(2, 3), "geodesic_propagation": stage_serial(3, 4),
+                       "whole_call": stage_serial(0, 4)}
+    for e in ev_s:
         for h in e:
             L.gf_event_destroy(h)
 
@@ -323,19 +346,24 @@ def run_ours(args):
     R = statistics.mean(reach) if reach else 0
     b_geo = 4.0 * Q * N + (R + Q) * Kn * 12.0 + 4.0 * R  # per reached pair 12K+4 B, + dense output
     peak, peak_src = measured_peak()
-    t_lv = stage_ms["geodesic_levels"]
+    t_lv = stage_ms["geodesic_propagation"]
+    t_alone = stage_ms_serial["geodesic_propagation"]
     achieved = (b_geo / (t_lv * 1e-3)) / 1e9 if t_lv else None
-    roofline = {"bound": "hbm", "kernel": "geo_levels_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    achieved_alone = (b_geo / (t_alone * 1e-3)) / 1e9 if t_alone else None
+    roofline = {"bound": "hbm", "kernel": "geo_seed_bfs_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_geo, "reached_pairs_R": R, "levels": max(levels) if levels else None,
-                "kernel_ms": t_lv,
+                "kernel_ms": t_lv, "kernel_ms_alone": t_alone, "achieved_alone": achieved_alone,
+                "frac_alone": (achieved_alone / peak) if achieved_alone else None,
+                "note": "kernel_ms is measured inside the timed region, where %d scenes are in flight and the kernel "
+                        "shares the SMs with the next scenes' FPS / kNN kernels; *_alone = serial pass" % nstreams,
                 "compulsory_bytes": 12.0 * N + 8.0 * N * k + 4.0 * Q * N}
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------
     e2e = None
     if not args.no_e2e:
         pinned = [x.pin_memory() for x in scenes_host]
-        nthreads = 2
+        nthreads = 3
         hgs = [HostGuidance(N, Q, k, cfg["radius"], cfg["max_step"], device=dev) for _ in range(nthreads)]
         Ke = max(4, min(K, 32))
         for h in hgs:
@@ -383,7 +411,7 @@ def run_ours(args):
                 "l2": "%d rotating scenes per rank, %.0f MB footprint each (> 126 MB L2 in total)" % (S, per_scene / 1e6),
                 "streams": nstreams}),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "stage_ms": stage_ms, "scenes_per_s": value / Q,
+            "stage_ms": stage_ms, "stage_ms_serial": stage_ms_serial, "scenes_per_s": value / Q,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
