@@ -1,0 +1,57 @@
+"""Multi-GPU tests (need >= 2 CUDA devices; skipped otherwise): NCCL process groups, one rank per GPU.
+seed-sharded propagation + all-gather == the single-GPU result, scene-parallel ownership, bit for bit."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from geoformer_b200.guidance import geodesic_guidance
+        from geoformer_b200.parallel import scene_parallel_guidance, seed_sharded_guidance, shard_scenes
+        from geoformer_b200.scenes import scene
+
+        x = scene(60_000, 5).to(dev)
+        for Q in (64, 37):  # even and ragged seed blocks
+            seeds, geo = seed_sharded_guidance(x, Q, 16, 0.5, 24)
+            ref_seeds, ref_geo = geodesic_guidance(x, Q, 16, 0.5, 24)
+            assert torch.equal(seeds, ref_seeds)
+            assert geo.shape == (Q, 60_000) and torch.equal(geo, ref_geo)
+        scenes = [scene(20_000 + 1000 * s, 30 + s).to(dev) for s in range(5)]
+        mine = scene_parallel_guidance(scenes, 32, 8, 0.5, 16)
+        assert sorted(mine) == shard_scenes(5, rank, world)
+        for s, (sd, g) in mine.items():
+            rs, rg = geodesic_guidance(scenes[s], 32, 8, 0.5, 16)
+            assert torch.equal(sd, rs) and torch.equal(g, rg)
+        dist.barrier()
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_seed_sharded_and_scene_parallel_nccl(tmp_path, cuda_lib):
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(world, 4)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / ("ok%d" % r)) for r in range(world))
