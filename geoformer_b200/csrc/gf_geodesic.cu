@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
   int *q1 = q0 + GEO_QCAP;
   uint32_t *vis = reinterpret_cast<uint32_t *>(q1 + GEO_QCAP);
   uint32_t *clm = vis + a.bitmap_words;
-  __shared__ int s_next_n, s_seed_q;
+  __shared__ int s_next_n[2], s_seed_q;  // next-frontier counter, by level parity
 
   const int N = a.N;
   const unsigned sb = (unsigned)a.slot_bits, KP = 1u << sb;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
     const bool seed_ok = s >= 0 && s < N;  // the reference would raise an index error; the row stays -1
     __syncthreads();
     if (tid == 0) {
-      s_next_n = 0;
+      s_next_n[0] = s_next_n[1] = 0;
       if (BITMAP) vis[(unsigned)N >> 5] |= 1u << (N & 31);
     }
     // frontier of level 1 = {seed}, padded with the sentinel point N
@@ -176,8 +176,36 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
     // NOTE the seed is NOT marked visited before level 1: the reference's first expansion has no
     // visited filter (:123), so a seed that appears in its own neighbour row is re-won at level 1.
     int level = 0;
+    // Distance of a point won at level `won`: the key left in its row entry is the reference's winner.
+    // level 1: the distance is the edge itself (:127); later: edge + parent's distance (:144)
+    auto resolve_finish = [&](int t, uint32_t key, int won) {
+      const unsigned p = (key & 0x7fffffffu) >> sb, j = key & (KP - 1);
+      const float w = __int_as_float(__ldg(a.edges + ((size_t)p << sb) + j).y);
+      row[t] = won == 1 ? w : __fadd_rn(w, __uint_as_float(ld_cg_u32(rowu + p)));  // :139
+    };
+    auto frontier_at = [&](const int *q, int i, int won) { return i < GEO_QCAP ? q[i] : ovf[ovf_index(i, won & 1, N)]; };
     while (F > 0 && level < a.max_step) {
       ++level;
+      // The points of this frontier were won at level-1 and still hold their keys.  Their distances are
+      // not needed to expand them, only to report them, so the resolve (two dependent L2 accesses) is
+      // started here, runs under the claims of pass A, and is finished after it.  (Without the on-chip
+      // bitmaps the visited test reads the row, so the row has to be resolved first.)
+      int rt = -1;
+      uint32_t rkey = 0;
+      if (level > 1) {
+        if (BITMAP) {
+          if ((int)tid < F) {
+            rt = fq[tid];
+            rkey = ld_cg_u32(rowu + rt);
+          }
+        } else {
+          for (int i = tid; i < F; i += GEO_THREADS) {
+            const int t = frontier_at(fq, i, level - 1);
+            resolve_finish(t, ld_cg_u32(rowu + t), level - 1);
+          }
+          __syncthreads();
+        }
+      }
       // ---- pass A: claims ---------------------------------------------------------------------------
       const int Fs = F < GEO_QCAP ? F : GEO_QCAP;  // on-chip part (padded to whole batches with N)
       for (int n0 = (int)group; n0 < Fs; n0 += (int)ngroups * GEO_UNROLL) {
@@ -189,40 +217,40 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
         for (int u = 0; u < GEO_UNROLL; ++u) t[u] = __ldg(&erow[ps[u]].x);
 #pragma unroll
         for (int u = 0; u < GEO_UNROLL; ++u)
-          geo_claim<BITMAP>(keybase | ps[u], t[u], N, level, vis, clm, rowu, nq, ovf, &s_next_n);
+          geo_claim<BITMAP>(keybase | ps[u], t[u], N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
       }
       for (int node = GEO_QCAP + (int)group; node < F; node += (int)ngroups) {  // spilled tail (rare)
         const unsigned ps = (unsigned)ovf[ovf_index(node, (level - 1) & 1, N)] << sb;
-        geo_claim<BITMAP>(keybase | ps, __ldg(&erow[ps].x), N, level, vis, clm, rowu, nq, ovf, &s_next_n);
+        geo_claim<BITMAP>(keybase | ps, __ldg(&erow[ps].x), N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+      }
+      if (BITMAP && level > 1) {  // finish the resolve of the points won at level-1
+        if (rt >= 0) resolve_finish(rt, rkey, level - 1);
+        for (int i = tid + GEO_THREADS; i < F; i += GEO_THREADS) {
+          const int t = frontier_at(fq, i, level - 1);
+          resolve_finish(t, ld_cg_u32(rowu + t), level - 1);
+        }
       }
       __syncthreads();
-      // ---- pass B: the key left in the row entry of a new point is the reference's winner ------------
-      const int nextF = s_next_n;
-      for (int i = tid; i < nextF; i += GEO_THREADS) {
-        const int t = i < GEO_QCAP ? nq[i] : ovf[ovf_index(i, level & 1, N)];
-        const uint32_t key = ld_cg_u32(rowu + t);
-        const unsigned p = (key & 0x7fffffffu) >> sb, j = key & (KP - 1);
-        const float w = __int_as_float(__ldg(a.edges + ((size_t)p << sb) + j).y);
-        // level 1: the distance is the edge itself (:127); later: edge + parent's distance (:144)
-        row[t] = level == 1 ? w : __fadd_rn(w, __uint_as_float(ld_cg_u32(rowu + p)));  // :139
-        if (BITMAP) {                                                                    // :140
+      // ---- commit: the points claimed at this level become visited (:140); pad the new frontier -------
+      const int nextF = s_next_n[level & 1];
+      if (tid == 0) s_next_n[(level + 1) & 1] = 0;  // idle since the previous level's reads; used again after the barrier below
+      if (BITMAP) {
+        for (int i = tid; i < nextF; i += GEO_THREADS) {
+          const int t = frontier_at(nq, i, level);
           atomicOr(vis + ((unsigned)t >> 5), 1u << (t & 31));
           atomicAnd(clm + ((unsigned)t >> 5), ~(1u << (t & 31)));
         }
       }
-      // pad the new frontier to whole batches with the sentinel
       {
-        const int padded = ((nextF + (int)ngroups * GEO_UNROLL - 1) / ((int)ngroups * GEO_UNROLL)) * ((int)ngroups * GEO_UNROLL);
+        const int batch = (int)ngroups * GEO_UNROLL;
+        const int padded = ((nextF + batch - 1) / batch) * batch;
         for (int i = nextF + (int)tid; i < padded && i < GEO_QCAP; i += GEO_THREADS) nq[i] = N;
       }
-      __syncthreads();
-      if (tid == 0) {
-        s_next_n = 0;
-        if (level == 1) {
-          // the seed joins the visited set now; if no self edge re-won it, its distance stays 0
-          if (ld_cg_u32(rowu + s) == GEO_UNVISITED) row[s] = 0.f;
-          if (BITMAP) vis[(unsigned)s >> 5] |= 1u << (s & 31);
-        }
+      if (tid == 0 && level == 1) {
+        // the seed joins the visited set now; if no self edge re-won it, its distance stays 0
+        // (a re-won seed holds its key until it is resolved with the other level-1 points)
+        if (ld_cg_u32(rowu + s) == GEO_UNVISITED) row[s] = 0.f;
+        if (BITMAP) atomicOr(vis + ((unsigned)s >> 5), 1u << (s & 31));
       }
       if (nextF > 0) deepest = level > deepest ? level : deepest;
       reached_total += (unsigned long long)nextF;
@@ -231,6 +259,13 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
       fq = nq;
       nq = tq;
       __syncthreads();
+    }
+    // the points won at the last executed level still hold their keys
+    if (level >= 1) {
+      for (int i = tid; i < F; i += GEO_THREADS) {
+        const int t = frontier_at(fq, i, level);
+        resolve_finish(t, ld_cg_u32(rowu + t), level);
+      }
     }
     if (level == 0 && seed_ok && tid == 0) row[s] = 0.f;  // max_step <= 0: only the seed entry (:118)
   }
