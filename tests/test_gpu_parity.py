@@ -71,14 +71,16 @@ def test_fps_config_c2_and_model_shape(oracle_lib, dev):
     assert len(set(out[0].tolist())) == 2048
 
 
-def test_fps_streaming_variant_large_scene(oracle_lib, dev):
-    """N above the on-chip capacity (c4-sized scene) takes the streaming kernel."""
+@pytest.mark.parametrize("B,N,m", [(1, 400_000, 24), (2, 250_000, 12), (1, 1_000_000, 16), (1, 1_300_000, 6)])
+def test_fps_whole_gpu_variants_large_scene(oracle_lib, dev, B, N, m):
+    """N above one cluster's register capacity: the cooperative whole-GPU kernel (points in registers up
+    to 1.2 M, streaming from L2 above), including a batch of two scenes."""
     from geoformer_b200.pointnet2 import _ext
     from geoformer_b200.scenes import room
 
-    xyz = room(400_000, 4321)[None]
-    ref = oracle_lib.furthest_point_sampling(xyz.numpy(), 24)
-    out = _ext.furthest_point_sampling(xyz.to(dev), 24).cpu().numpy()
+    xyz = torch.stack([room(N, 4321 + b) for b in range(B)])
+    ref = oracle_lib.furthest_point_sampling(xyz.numpy(), m)
+    out = _ext.furthest_point_sampling(xyz.to(dev), m).cpu().numpy()
     assert np.array_equal(out, ref)
 
 
