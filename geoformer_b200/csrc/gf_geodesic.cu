@@ -107,14 +107,20 @@ __device__ __forceinline__ void frontier_put(int *sq, int *ovf, int i, int level
 
 // one candidate edge p --(slot)--> t of the current level (t == N for padding / unusable edges)
 // key = 0x80000000 | p << SB | slot, passed in pre-assembled (the shift is shared with the row address)
-template <bool BITMAP>
+// MODE 2: visited + claimed bitmaps in shared memory (N <~ 800k); MODE 1: visited bitmap only, the first
+// claimant is told by the returning atomic (N <~ 1.7 M); MODE 0: no on-chip state, the row is the visited set.
+template <int MODE>
 __device__ __forceinline__ void geo_claim(uint32_t key, int t, int N, int level, uint32_t *vis, uint32_t *clm,
                                           uint32_t *rowu, int *nq, int *ovf, int *s_next_n) {
-  if (BITMAP) {
+  if (MODE >= 1) {
     const unsigned tw = (unsigned)t >> 5, tb = 1u << (t & 31);
-    if (vis[tw] & tb) return;             // visited, padding, or filtered edge
-    atomicMin(rowu + t, key);             // RED.MIN: fire and forget
-    if (atomicOr(clm + tw, tb) & tb) return;  // somebody claimed t earlier in this level
+    if (vis[tw] & tb) return;  // visited, padding, or filtered edge
+    if (MODE == 2) {
+      atomicMin(rowu + t, key);                 // RED.MIN: fire and forget
+      if (atomicOr(clm + tw, tb) & tb) return;  // somebody claimed t earlier in this level
+    } else {
+      if (atomicMin(rowu + t, key) != GEO_UNVISITED) return;
+    }
   } else {
     if (t >= N || ld_cg_u32(rowu + t) < GEO_KEYBIT) return;
     if (atomicMin(rowu + t, key) != GEO_UNVISITED) return;
@@ -122,8 +128,9 @@ __device__ __forceinline__ void geo_claim(uint32_t key, int t, int N, int level,
   frontier_put(nq, ovf, atomicAdd(s_next_n, 1), level & 1, N, t);  // first claimant: t joins the next frontier
 }
 
-template <bool BITMAP>
+template <int MODE>
 __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoArgs a) {
+  constexpr bool BITMAP = MODE >= 1;  // a visited bitmap lives in shared memory
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int *q0 = reinterpret_cast<int *>(smem_raw);
   int *q1 = q0 + GEO_QCAP;
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
       const size_t tail0 = h + nvec * 4;
       if ((size_t)tid < (size_t)N - tail0) row[tail0 + tid] = -1.f;
       if (BITMAP)
-        for (int i = tid; i < 2 * a.bitmap_words; i += GEO_THREADS) vis[i] = 0u;  // vis and clm are contiguous
+        for (int i = tid; i < (MODE == 2 ? 2 : 1) * a.bitmap_words; i += GEO_THREADS) vis[i] = 0u;  // vis, clm contiguous
     }
     const int s = a.seeds[q];
     const bool seed_ok = s >= 0 && s < N;  // the reference would raise an index error; the row stays -1
@@ -217,11 +224,11 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
         for (int u = 0; u < GEO_UNROLL; ++u) t[u] = __ldg(&erow[ps[u]].x);
 #pragma unroll
         for (int u = 0; u < GEO_UNROLL; ++u)
-          geo_claim<BITMAP>(keybase | ps[u], t[u], N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+          geo_claim<MODE>(keybase | ps[u], t[u], N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
       }
       for (int node = GEO_QCAP + (int)group; node < F; node += (int)ngroups) {  // spilled tail (rare)
         const unsigned ps = (unsigned)ovf[ovf_index(node, (level - 1) & 1, N)] << sb;
-        geo_claim<BITMAP>(keybase | ps, __ldg(&erow[ps].x), N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+        geo_claim<MODE>(keybase | ps, __ldg(&erow[ps].x), N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
       }
       if (BITMAP && level > 1) {  // finish the resolve of the points won at level-1
         if (rt >= 0) resolve_finish(rt, rkey, level - 1);
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
         for (int i = tid; i < nextF; i += GEO_THREADS) {
           const int t = frontier_at(nq, i, level);
           atomicOr(vis + ((unsigned)t >> 5), 1u << (t & 31));
-          atomicAnd(clm + ((unsigned)t >> 5), ~(1u << (t & 31)));
+          if (MODE == 2) atomicAnd(clm + ((unsigned)t >> 5), ~(1u << (t & 31)));
         }
       }
       {
@@ -282,35 +289,38 @@ static int ceil_log2(int v) {
 }
 
 struct GeoPlan {
-  int grid, bitmap_words;
+  int grid, bitmap_words, mode;
   size_t smem;
 };
 
 // shared-memory plan, identical for sizing and launching: 227 KB usable per CTA and per SM on sm_100
-static void geo_smem_plan(int N, int *bitmap_words, size_t *smem, int *ctas_per_sm) {
+static void geo_smem_plan(int N, int *bitmap_words, size_t *smem, int *ctas_per_sm, int *mode) {
   const size_t fixed = sizeof(int) * 2 * GEO_QCAP;
-  int words = (N + 1 + 31) / 32;  // + the sentinel point N
-  size_t bytes = fixed + sizeof(uint32_t) * 2 * (size_t)words;
-  static int no_bitmap = -1;
-  if (no_bitmap < 0) {
-    const char *e = getenv("GF_GEO_NOBITMAP");  // test knob: force the large-scene variant
-    no_bitmap = e ? atoi(e) : 0;
+  const int words = (N + 1 + 31) / 32;  // + the sentinel point N
+  static int max_mode = -1;
+  if (max_mode < 0) {
+    const char *e = getenv("GF_GEO_NOBITMAP");  // test knob: 1 = no on-chip state, 2 = visited bitmap only
+    const int v = e ? atoi(e) : 0;
+    max_mode = v == 1 ? 0 : (v == 2 ? 1 : 2);
   }
-  if (no_bitmap || bytes > (size_t)226 * 1024) {  // no on-chip bitmaps: test / claim through the row
-    words = 0;
-    bytes = fixed;
-  }
+  int m = max_mode;
+  // both bitmaps must fit for mode 2; otherwise mode 0 (two CTAs per SM) measured slightly faster at 1 M
+  // points than mode 1 (157 KB of shared memory: one CTA per SM), which stays available through the knob
+  if (m == 2 && fixed + sizeof(uint32_t) * 2 * (size_t)words > (size_t)226 * 1024) m = 0;
+  if (m == 1 && fixed + sizeof(uint32_t) * (size_t)words > (size_t)226 * 1024) m = 0;
+  const size_t bytes = fixed + sizeof(uint32_t) * (size_t)m * words;
   int per_sm = (int)((size_t)(227 * 1024) / (bytes + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 2) per_sm = 2;  // __launch_bounds__(GEO_THREADS, 2)
-  *bitmap_words = words;
+  *bitmap_words = m > 0 ? words : 0;
   *smem = bytes;
   *ctas_per_sm = per_sm;
+  *mode = m;
 }
 
 static int plan_geo(int N, int Q, GeoPlan *p) {
   int per_sm = 1;
-  geo_smem_plan(N, &p->bitmap_words, &p->smem, &per_sm);
+  geo_smem_plan(N, &p->bitmap_words, &p->smem, &per_sm, &p->mode);
   static int bps_cap = -1;
   if (bps_cap < 0) {
     const char *e = getenv("GF_GEO_BPS");  // experiment knob
@@ -324,9 +334,9 @@ static int plan_geo(int N, int Q, GeoPlan *p) {
 }
 
 size_t geodesic_workspace_bytes(int N, int k, int Q) {
-  int words = 0, per_sm = 1;
+  int words = 0, per_sm = 1, mode = 0;
   size_t smem = 0;
-  geo_smem_plan(N, &words, &smem, &per_sm);
+  geo_smem_plan(N, &words, &smem, &per_sm, &mode);
   long long grid = (long long)num_sms() * per_sm;
   if (grid > Q) grid = Q;
   if (grid < 1) grid = 1;
@@ -385,13 +395,19 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
   cudaMemsetAsync(d_trace, 0, 8 * 4 * 300, st);
   ga.trace = d_trace;
 #endif
-  if (p.bitmap_words) {
-    GF_CUDA(cudaFuncSetAttribute(geo_seed_bfs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    geo_seed_bfs_kernel<true><<<p.grid, GEO_THREADS, p.smem, st>>>(ga);
-  } else {
-    GF_CUDA(cudaFuncSetAttribute(geo_seed_bfs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    geo_seed_bfs_kernel<false><<<p.grid, GEO_THREADS, p.smem, st>>>(ga);
-  }
+#define GF_GEO_LAUNCH(M)                                                                                      \
+  do {                                                                                                        \
+    GF_CUDA(cudaFuncSetAttribute(geo_seed_bfs_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                 (int)p.smem));                                                               \
+    geo_seed_bfs_kernel<M><<<p.grid, GEO_THREADS, p.smem, st>>>(ga);                                          \
+  } while (0)
+  if (p.mode == 2)
+    GF_GEO_LAUNCH(2);
+  else if (p.mode == 1)
+    GF_GEO_LAUNCH(1);
+  else
+    GF_GEO_LAUNCH(0);
+#undef GF_GEO_LAUNCH
   GF_LAUNCHED();
 #ifdef GF_TRACE
   {
