@@ -40,14 +40,14 @@ namespace gf {
 
 constexpr int GEO_THREADS = 1024;
 constexpr int GEO_QCAP = 4096;  // frontier entries kept in shared memory (per buffer)
-constexpr int GEO_UNROLL = 4;
+constexpr int GEO_UNROLL = 2;  // frontier points in flight per lane group (x 4 edges per lane)
 constexpr uint32_t GEO_UNVISITED = 0xBF800000u;  // bits of -1.0f
 constexpr uint32_t GEO_KEYBIT = 0x80000000u;
 constexpr uint32_t GEO_KEYMAX = 0x3F800000u;  // row-claim keys must stay below "unvisited"
-constexpr int GEO_EMPTY = -1;
 
 struct GeoArgs {
-  const int2 *edges;  // (N + 1, KP) packed {target, length bits}; unusable edges and row N point to N
+  const int *tgt;   // (N + 1, KP) edge targets; unusable edges and the sentinel row N point to N
+  const float *len;  // (N + 1, KP) edge lengths (read only when a winner is resolved)
   int N, Q, max_step;
   int slot_bits;  // KP = 1 << slot_bits
   const int *seeds;
@@ -68,25 +68,28 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
 }
 
 // ---- edge packing ---------------------------------------------------------------------------------
-// edges[p][j] = {I[p][1+j], D[p][1+j]} if the edge may ever be used (D <= radius, 0 <= I < N;
-// geodesic_utils.py:123,151), else {N, 0}; column 0 of the kNN result is dropped (:110-111).
-// Row N (the sentinel point used to pad frontier queues) has only edges to N.
+// tgt[p][j], len[p][j] = I[p][1+j], D[p][1+j] if the edge may ever be used (D <= radius, 0 <= I < N;
+// geodesic_utils.py:123,151), else N, 0; column 0 of the kNN result is dropped (:110-111).
+// Row N (the sentinel point used to pad frontier queues) has only edges to N.  KP >= 4 so that a
+// lane can fetch four targets with one 16-byte load.
 template <bool IS64>
 __global__ void geo_pack_edges_kernel(const float *__restrict__ D, const void *__restrict__ I, int N, int k,
-                                      float radius, int slot_bits, int2 *__restrict__ edges) {
+                                      float radius, int slot_bits, int *__restrict__ tgt, float *__restrict__ len) {
   const int KP = 1 << slot_bits, K = k - 1;
   const long long total = ((long long)N + 1) << slot_bits;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(e >> slot_bits), j = (int)(e & (KP - 1));
-    int2 out = make_int2(N, 0);
+    int to = N;
+    float wo = 0.f;
     if (j < K && p < N) {
       const size_t at = (size_t)p * k + 1 + j;
       const long long t = IS64 ? ((const long long *)I)[at] : (long long)((const int *)I)[at];
       const float w = __ldg(D + at);
-      if (w <= radius && t >= 0 && t < N) out = make_int2((int)t, __float_as_int(w));
+      if (w <= radius && t >= 0 && t < N) to = (int)t, wo = w;
     }
-    edges[e] = out;
+    tgt[e] = to;
+    len[e] = wo;
   }
 }
 
@@ -141,9 +144,11 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
   const int N = a.N;
   const unsigned sb = (unsigned)a.slot_bits, KP = 1u << sb;
   const unsigned tid = threadIdx.x;
-  const unsigned slot = tid & (KP - 1), group = tid >> sb, ngroups = GEO_THREADS >> sb;
-  const int2 *__restrict__ erow = a.edges + slot;  // + (p << sb): this lane's column of the edge rows
-  const uint32_t keybase = GEO_KEYBIT | slot;
+  // a group of KP/4 lanes expands one frontier point: each lane fetches four targets with one 16-byte load
+  const unsigned lsb = sb - 2, sub = tid & ((1u << lsb) - 1u);
+  const unsigned group = tid >> lsb, ngroups = GEO_THREADS >> lsb;
+  const int4 *__restrict__ trow = reinterpret_cast<const int4 *>(a.tgt) + sub;  // + (p << lsb)
+  const uint32_t keybase = GEO_KEYBIT | (sub << 2);
   int *ovf = a.overflow + (size_t)blockIdx.x * ((size_t)N + 2);
   unsigned long long reached_total = 0;
   int deepest = 0;
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
     // level 1: the distance is the edge itself (:127); later: edge + parent's distance (:144)
     auto resolve_finish = [&](int t, uint32_t key, int won) {
       const unsigned p = (key & 0x7fffffffu) >> sb, j = key & (KP - 1);
-      const float w = __int_as_float(__ldg(a.edges + ((size_t)p << sb) + j).y);
+      const float w = __ldg(a.len + ((size_t)p << sb) + j);
       row[t] = won == 1 ? w : __fadd_rn(w, __uint_as_float(ld_cg_u32(rowu + p)));  // :139
     };
     auto frontier_at = [&](const int *q, int i, int won) { return i < GEO_QCAP ? q[i] : ovf[ovf_index(i, won & 1, N)]; };
@@ -216,19 +221,29 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
       // ---- pass A: claims ---------------------------------------------------------------------------
       const int Fs = F < GEO_QCAP ? F : GEO_QCAP;  // on-chip part (padded to whole batches with N)
       for (int n0 = (int)group; n0 < Fs; n0 += (int)ngroups * GEO_UNROLL) {
-        unsigned ps[GEO_UNROLL];  // p << sb: 32-bit, (N + 1) << sb < 2^30 by the host-side key check
-        int t[GEO_UNROLL];
+        unsigned pl[GEO_UNROLL];  // p << lsb: 32-bit, (N + 1) << sb < 2^30 by the host-side key check
+        int4 t[GEO_UNROLL];
 #pragma unroll
-        for (int u = 0; u < GEO_UNROLL; ++u) ps[u] = (unsigned)fq[n0 + u * (int)ngroups] << sb;
+        for (int u = 0; u < GEO_UNROLL; ++u) pl[u] = (unsigned)fq[n0 + u * (int)ngroups] << lsb;
 #pragma unroll
-        for (int u = 0; u < GEO_UNROLL; ++u) t[u] = __ldg(&erow[ps[u]].x);
+        for (int u = 0; u < GEO_UNROLL; ++u) t[u] = __ldg(trow + pl[u]);
 #pragma unroll
-        for (int u = 0; u < GEO_UNROLL; ++u)
-          geo_claim<MODE>(keybase | ps[u], t[u], N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+        for (int u = 0; u < GEO_UNROLL; ++u) {
+          const uint32_t key = keybase | (pl[u] << 2);
+          geo_claim<MODE>(key + 0, t[u].x, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+          geo_claim<MODE>(key + 1, t[u].y, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+          geo_claim<MODE>(key + 2, t[u].z, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+          geo_claim<MODE>(key + 3, t[u].w, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+        }
       }
       for (int node = GEO_QCAP + (int)group; node < F; node += (int)ngroups) {  // spilled tail (rare)
-        const unsigned ps = (unsigned)ovf[ovf_index(node, (level - 1) & 1, N)] << sb;
-        geo_claim<MODE>(keybase | ps, __ldg(&erow[ps].x), N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+        const unsigned pl = (unsigned)ovf[ovf_index(node, (level - 1) & 1, N)] << lsb;
+        const int4 t = __ldg(trow + pl);
+        const uint32_t key = keybase | (pl << 2);
+        geo_claim<MODE>(key + 0, t.x, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+        geo_claim<MODE>(key + 1, t.y, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+        geo_claim<MODE>(key + 2, t.z, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+        geo_claim<MODE>(key + 3, t.w, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
       }
       if (BITMAP && level > 1) {  // finish the resolve of the points won at level-1
         if (rt >= 0) resolve_finish(rt, rkey, level - 1);
@@ -287,6 +302,11 @@ static int ceil_log2(int v) {
   while ((1 << b) < v) ++b;
   return b;
 }
+// edge rows are padded to KP = 2^slot_bits >= 4 entries (four targets per 16-byte load)
+static int geo_slot_bits(int k) {
+  const int sb = ceil_log2(k - 1 > 1 ? k - 1 : 1);
+  return sb < 2 ? 2 : sb;
+}
 
 struct GeoPlan {
   int grid, bitmap_words, mode;
@@ -340,9 +360,9 @@ size_t geodesic_workspace_bytes(int N, int k, int Q) {
   long long grid = (long long)num_sms() * per_sm;
   if (grid > Q) grid = Q;
   if (grid < 1) grid = 1;
-  const int sb = ceil_log2(k - 1 > 1 ? k - 1 : 1);
+  const int sb = geo_slot_bits(k);
   size_t b = 0;
-  b += align256(sizeof(int2) * (((size_t)N + 1) << sb));        // packed edges (+ sentinel row)
+  b += align256(sizeof(int) * (((size_t)N + 1) << sb)) * 2;     // packed edge targets + lengths (+ sentinel row)
   b += align256(sizeof(int) * ((size_t)N + 2) * (size_t)grid);  // frontier overflow
   b += align256(64);                                             // seed counter
   b += align256(64);                                             // stats
@@ -352,17 +372,17 @@ size_t geodesic_workspace_bytes(int N, int k, int Q) {
 int geodesic_run(const float *D, const void *I, int is64, int N, int k, const int *seeds, int Q, float radius,
                  int max_step, float *geo, int64_t *stats_out, void *workspace, size_t workspace_bytes,
                  cudaStream_t st) {
-  const int K = k - 1;
   GeoPlan p;
   int rc = plan_geo(N, Q, &p);
   if (rc) return rc;
-  const int slot_bits = ceil_log2(K > 1 ? K : 1);
+  const int slot_bits = geo_slot_bits(k);
   if ((((unsigned long long)N + 1) << slot_bits) >= GEO_KEYMAX) {
     set_error("geodesic: N=%d with k=%d does not fit the 30-bit claim key (N << %d must be < 2^30)", N, k, slot_bits);
     return GF_ERR_INVALID;
   }
   Arena a(workspace, workspace_bytes);
-  int2 *edges = a.take<int2>(((size_t)N + 1) << slot_bits);
+  int *tgt = a.take<int>(((size_t)N + 1) << slot_bits);
+  float *len = a.take<float>(((size_t)N + 1) << slot_bits);
   int *overflow = a.take<int>(((size_t)N + 2) * (size_t)p.grid);
   unsigned *counter = a.take<unsigned>(16);
   unsigned long long *stats = a.take<unsigned long long>(8);
@@ -379,14 +399,14 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
     const long long cap = (long long)num_sms() * 16;
     const int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
     if (is64)
-      geo_pack_edges_kernel<true><<<grid, 256, 0, st>>>(D, I, N, k, radius, slot_bits, edges);
+      geo_pack_edges_kernel<true><<<grid, 256, 0, st>>>(D, I, N, k, radius, slot_bits, tgt, len);
     else
-      geo_pack_edges_kernel<false><<<grid, 256, 0, st>>>(D, I, N, k, radius, slot_bits, edges);
+      geo_pack_edges_kernel<false><<<grid, 256, 0, st>>>(D, I, N, k, radius, slot_bits, tgt, len);
     GF_LAUNCHED();
   }
   stage_mark(ST_GEO_READY, st);
   GeoArgs ga;
-  ga.edges = edges, ga.N = N, ga.Q = Q, ga.max_step = max_step, ga.slot_bits = slot_bits;
+  ga.tgt = tgt, ga.len = len, ga.N = N, ga.Q = Q, ga.max_step = max_step, ga.slot_bits = slot_bits;
   ga.seeds = seeds, ga.geo = geo, ga.overflow = overflow, ga.seed_counter = counter, ga.stats = stats;
   ga.bitmap_words = p.bitmap_words;
 #ifdef GF_TRACE
