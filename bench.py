@@ -359,6 +359,43 @@ def run_ours(args):
                         "shares the SMs with the next scenes' FPS / kNN kernels; *_alone = serial pass" % nstreams,
                 "compulsory_bytes": 12.0 * N + 8.0 * N * k + 4.0 * Q * N}
 
+    # ---- the two distance -> bias epilogues, timed on their own ---------------------
+    epilogues = None
+    try:
+        from geoformer_b200.bias import decoder_relative_pos, mask_head_relative_coords
+        from geoformer_b200.pointnet2 import _ext as p2
+
+        Cn = 2048  # contexts of the real model (geoformer_fs.py:630-645); the seeds are their prefix
+        ctx = p2.furthest_point_sampling(xs[0][None].contiguous(), Cn)
+        geo0 = runners[0].geo if S == 1 else runners[0].run(xs[0], stream)[1]
+        ctx_xyz = xs[0][ctx[0].long()][None].contiguous()
+        q_xyz = ctx_xyz[:, :Q].contiguous()
+        torch.cuda.synchronize(dev)
+
+        def timeit(fn, reps=10):
+            fn()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(stream)
+            for _ in range(reps):
+                fn()
+            b_.record(stream)
+            torch.cuda.synchronize(dev)
+            return a_.elapsed_time(b_) / reps
+
+        t_dec = timeit(lambda: decoder_relative_pos([geo0], ctx, q_xyz, ctx_xyz))
+        t_mask = timeit(lambda: mask_head_relative_coords(geo0, xs[0], q_xyz[0]))
+        b_dec = 4.0 * Q * Cn * (1 + 3)            # gather + (B,Q,C,3) write
+        b_mask = 4.0 * Q * N * (1 + 3) + 12.0 * N  # one read of geo + (Q,3,N) write + coords
+        epilogues = {
+            "decoder_bias": {"ms": t_dec, "algorithmic_bytes": b_dec, "GBps": b_dec / t_dec / 1e6},
+            "mask_head_bias": {"ms": t_mask, "algorithmic_bytes": b_mask, "GBps": b_mask / t_mask / 1e6,
+                               "frac_of_hbm_peak": b_mask / t_mask / 1e6 / peak,
+                               "note": "timed through the Python call incl. output allocation; the kernel reads geo "
+                                       "twice (row max, then the element-wise pass)"},
+        }
+    except Exception as ex:
+        epilogues = {"error": repr(ex)}
+
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -411,7 +448,7 @@ def run_ours(args):
                 "l2": "%d rotating scenes per rank, %.0f MB footprint each (> 126 MB L2 in total)" % (S, per_scene / 1e6),
                 "streams": nstreams}),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "stage_ms": stage_ms, "stage_ms_serial": stage_ms_serial, "scenes_per_s": value / Q,
+            "stage_ms": stage_ms, "stage_ms_serial": stage_ms_serial, "epilogues": epilogues, "scenes_per_s": value / Q,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -60,24 +60,45 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---- mask-head epilogue -----------------------------------------------------------------------------
+// Pure streaming (read geo, write three times as much): 16-byte accesses, four points per thread.
 // rowmax[q] = max_p geo[q,p]   (:274-275); several CTAs per row, combined with an ordered atomicMax
+template <bool VEC>
 __global__ void __launch_bounds__(256)
     bias_mask_rowmax_kernel(const float *__restrict__ geo, int N, int chunks, uint32_t *__restrict__ rowmax_ord,
                             uint32_t *__restrict__ gmax) {
   __shared__ float sm[8];
   const int q = blockIdx.x / chunks, ch = blockIdx.x - q * chunks;
-  const int per = (N + chunks - 1) / chunks;
-  const int p0 = ch * per, p1 = min(N, p0 + per);
+  const float *row = geo + (size_t)q * N;
   float v = -__int_as_float(0x7f800000);
-  for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) v = fmaxf(v, __ldg(geo + (size_t)q * N + p));
+  if (VEC) {
+    const int n4 = N >> 2, per = (n4 + chunks - 1) / chunks;
+    const int p0 = ch * per, p1 = min(n4, p0 + per);
+    const float4 *r4 = reinterpret_cast<const float4 *>(row);
+    for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+      const float4 g = __ldg(r4 + p);
+      v = fmaxf(fmaxf(v, fmaxf(g.x, g.y)), fmaxf(g.z, g.w));
+    }
+  } else {
+    const int per = (N + chunks - 1) / chunks;
+    const int p0 = ch * per, p1 = min(N, p0 + per);
+    for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) v = fmaxf(v, __ldg(row + p));
+  }
   float r = block_max(v, sm);
-  if (threadIdx.x == 0 && p0 < p1) {
+  if (threadIdx.x == 0 && r > -__int_as_float(0x7f800000)) {
     atomicMax(rowmax_ord + q, f2ord(r));
     atomicMax(gmax, f2ord(r));
   }
 }
 
+__device__ __forceinline__ float mask_push(float d, float s, bool unreached) {
+  // d + sqrt(rowmax) * sign(d) where the point is unreachable (:284-286); torch.sign: 0 -> 0, NaN -> NaN
+  if (!unreached) return d;
+  const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : d);
+  return __fadd_rn(d, __fmul_rn(s, sg));
+}
+
 // out[q,a,p] = d + (geo[q,p] < 0 ? sqrt(m_q) * sign(d) : 0),  d = seed_xyz[q,a] - coords[p,a]   (:271-289)
+template <bool VEC>
 __global__ void __launch_bounds__(256)
     bias_mask_write_kernel(const float *__restrict__ geo, const float *__restrict__ coords,
                            const float *__restrict__ seed_xyz, int Q, int N, const uint32_t *__restrict__ rowmax_ord,
@@ -88,22 +109,37 @@ __global__ void __launch_bounds__(256)
   const float s = sqrtf(m);       // :277
   const float sx = seed_xyz[q * 3 + 0], sy = seed_xyz[q * 3 + 1], sz = seed_xyz[q * 3 + 2];
   float *o = out + (size_t)q * 3 * N;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
-    float g = __ldg(geo + (size_t)q * N + p);
-    float dx = __fsub_rn(sx, __ldg(coords + (size_t)p * 3 + 0));
-    float dy = __fsub_rn(sy, __ldg(coords + (size_t)p * 3 + 1));
-    float dz = __fsub_rn(sz, __ldg(coords + (size_t)p * 3 + 2));
-    if (g < 0.f) {
-      float gx = dx > 0.f ? 1.f : (dx < 0.f ? -1.f : dx);  // torch.sign: 0 -> 0, NaN -> NaN
-      float gy = dy > 0.f ? 1.f : (dy < 0.f ? -1.f : dy);
-      float gz = dz > 0.f ? 1.f : (dz < 0.f ? -1.f : dz);
-      dx = __fadd_rn(dx, __fmul_rn(s, gx));
-      dy = __fadd_rn(dy, __fmul_rn(s, gy));
-      dz = __fadd_rn(dz, __fmul_rn(s, gz));
+  const float *row = geo + (size_t)q * N;
+  if (VEC) {
+    const int n4 = N >> 2;
+    const float4 *g4 = reinterpret_cast<const float4 *>(row);
+    const float4 *c4 = reinterpret_cast<const float4 *>(coords);  // 4 points = 12 floats = 3 float4
+    float4 *ox = reinterpret_cast<float4 *>(o), *oy = reinterpret_cast<float4 *>(o + N),
+           *oz = reinterpret_cast<float4 *>(o + 2 * (size_t)N);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n4; p += gridDim.x * blockDim.x) {
+      const float4 g = __ldg(g4 + p);
+      const float4 a = __ldg(c4 + 3 * (size_t)p), b = __ldg(c4 + 3 * (size_t)p + 1), c = __ldg(c4 + 3 * (size_t)p + 2);
+      // a = x0 y0 z0 x1 | b = y1 z1 x2 y2 | c = z2 x3 y3 z3
+      float4 rx, ry, rz;
+      rx.x = mask_push(__fsub_rn(sx, a.x), s, g.x < 0.f), ry.x = mask_push(__fsub_rn(sy, a.y), s, g.x < 0.f),
+      rz.x = mask_push(__fsub_rn(sz, a.z), s, g.x < 0.f);
+      rx.y = mask_push(__fsub_rn(sx, a.w), s, g.y < 0.f), ry.y = mask_push(__fsub_rn(sy, b.x), s, g.y < 0.f),
+      rz.y = mask_push(__fsub_rn(sz, b.y), s, g.y < 0.f);
+      rx.z = mask_push(__fsub_rn(sx, b.z), s, g.z < 0.f), ry.z = mask_push(__fsub_rn(sy, b.w), s, g.z < 0.f),
+      rz.z = mask_push(__fsub_rn(sz, c.x), s, g.z < 0.f);
+      rx.w = mask_push(__fsub_rn(sx, c.y), s, g.w < 0.f), ry.w = mask_push(__fsub_rn(sy, c.z), s, g.w < 0.f),
+      rz.w = mask_push(__fsub_rn(sz, c.w), s, g.w < 0.f);
+      __stcs(ox + p, rx);  // written once, never re-read by this kernel: streaming stores
+      __stcs(oy + p, ry);
+      __stcs(oz + p, rz);
     }
-    o[p] = dx;
-    o[(size_t)N + p] = dy;
-    o[(size_t)2 * N + p] = dz;
+  } else {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+      const bool un = __ldg(row + p) < 0.f;
+      o[p] = mask_push(__fsub_rn(sx, __ldg(coords + (size_t)p * 3 + 0)), s, un);
+      o[(size_t)N + p] = mask_push(__fsub_rn(sy, __ldg(coords + (size_t)p * 3 + 1)), s, un);
+      o[(size_t)2 * N + p] = mask_push(__fsub_rn(sz, __ldg(coords + (size_t)p * 3 + 2)), s, un);
+    }
   }
 }
 
@@ -164,16 +200,26 @@ extern "C" int gf_bias_mask_head(const float *geo, const float *coords, const fl
   GF_CUDA(cudaMemsetAsync(rowmax, 0, sizeof(uint32_t) * (size_t)Q, st));
   bias_init_kernel<<<1, 1, 0, st>>>(gmax);
   GF_LAUNCHED();
+  // 16-byte path: N a multiple of 4 and all bases 16-byte aligned (torch allocations are)
+  const bool vec = (N % 4 == 0) && ((((uintptr_t)geo | (uintptr_t)coords | (uintptr_t)out) & 15) == 0);
+  const int work = vec ? N / 4 : N;
   int chunks = (num_sms() * 8 + Q - 1) / Q;
   if (chunks < 1) chunks = 1;
-  if (chunks > (N + 1023) / 1024) chunks = (N + 1023) / 1024;
-  bias_mask_rowmax_kernel<<<Q * chunks, 256, 0, st>>>(geo, N, chunks, rowmax, gmax);
+  if (chunks > (work + 1023) / 1024) chunks = (work + 1023) / 1024;
+  if (chunks < 1) chunks = 1;
+  if (vec)
+    bias_mask_rowmax_kernel<true><<<Q * chunks, 256, 0, st>>>(geo, N, chunks, rowmax, gmax);
+  else
+    bias_mask_rowmax_kernel<false><<<Q * chunks, 256, 0, st>>>(geo, N, chunks, rowmax, gmax);
   GF_LAUNCHED();
-  int gx = (N + 255) / 256;
+  int gx = (work + 255) / 256;
   int cap = (num_sms() * 16 + Q - 1) / Q;
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
-  bias_mask_write_kernel<<<dim3(gx, Q), 256, 0, st>>>(geo, coords, seed_xyz, Q, N, rowmax, gmax, out);
+  if (vec)
+    bias_mask_write_kernel<true><<<dim3(gx, Q), 256, 0, st>>>(geo, coords, seed_xyz, Q, N, rowmax, gmax, out);
+  else
+    bias_mask_write_kernel<false><<<dim3(gx, Q), 256, 0, st>>>(geo, coords, seed_xyz, Q, N, rowmax, gmax, out);
   GF_LAUNCHED();
   return GF_OK;
 }
