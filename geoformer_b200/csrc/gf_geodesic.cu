@@ -119,8 +119,9 @@ __device__ __forceinline__ void geo_claim(uint32_t key, int t, int N, int level,
     const unsigned tw = (unsigned)t >> 5, tb = 1u << (t & 31);
     if (vis[tw] & tb) return;  // visited, padding, or filtered edge
     if (MODE == 2) {
-      atomicMin(rowu + t, key);                 // RED.MIN: fire and forget
-      if (atomicOr(clm + tw, tb) & tb) return;  // somebody claimed t earlier in this level
+      atomicMin(rowu + t, key);  // RED.MIN: fire and forget
+      atomicOr(clm + tw, tb);    // fire and forget too: the next frontier is read off this bitmap after the level
+      return;
     } else {
       if (atomicMin(rowu + t, key) != GEO_UNVISITED) return;
     }
@@ -160,6 +161,11 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
     if (q >= a.Q) break;
     float *row = a.geo + (size_t)q * N;
     uint32_t *rowu = reinterpret_cast<uint32_t *>(row);
+#ifdef GF_TRACE
+    long long tr_t0 = 0, tr_t1 = 0;
+    const unsigned long long tr_r0 = reached_total;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0));
+#endif
     {  // init: row = -1 (geodesic_utils.py:113), visited = claimed = {} (:114), sentinel bit N set
       const size_t head = ((16 - ((uintptr_t)row & 15)) & 15) / 4;
       const size_t h = head < (size_t)N ? head : (size_t)N;
@@ -180,8 +186,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
       s_next_n[0] = s_next_n[1] = 0;
       if (BITMAP) vis[(unsigned)N >> 5] |= 1u << (N & 31);
     }
-    // frontier of level 1 = {seed}, padded with the sentinel point N
-    for (int i = tid; i < (int)ngroups * GEO_UNROLL; i += GEO_THREADS) q0[i] = (i == 0 && seed_ok) ? s : N;
+    if (tid == 0) q0[0] = s;  // frontier of level 1 = {seed}
     __syncthreads();
     int F = seed_ok ? 1 : 0;
     int *fq = q0, *nq = q1;
@@ -219,12 +224,15 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
         }
       }
       // ---- pass A: claims ---------------------------------------------------------------------------
-      const int Fs = F < GEO_QCAP ? F : GEO_QCAP;  // on-chip part (padded to whole batches with N)
+      const int Fs = F < GEO_QCAP ? F : GEO_QCAP;  // on-chip part; lanes past the end expand the sentinel point N
       for (int n0 = (int)group; n0 < Fs; n0 += (int)ngroups * GEO_UNROLL) {
         unsigned pl[GEO_UNROLL];  // p << lsb: 32-bit, (N + 1) << sb < 2^30 by the host-side key check
         int4 t[GEO_UNROLL];
 #pragma unroll
-        for (int u = 0; u < GEO_UNROLL; ++u) pl[u] = (unsigned)fq[n0 + u * (int)ngroups] << lsb;
+        for (int u = 0; u < GEO_UNROLL; ++u) {
+          const int at = n0 + u * (int)ngroups;
+          pl[u] = (unsigned)(at < Fs ? fq[at] : N) << lsb;
+        }
 #pragma unroll
         for (int u = 0; u < GEO_UNROLL; ++u) t[u] = __ldg(trow + pl[u]);
 #pragma unroll
@@ -253,24 +261,42 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
         }
       }
       __syncthreads();
-      // ---- commit: the points claimed at this level become visited (:140); pad the new frontier -------
+      // ---- commit: the points claimed at this level become visited (:140) and form the next frontier ---
+      if (tid == 0) s_next_n[(level + 1) & 1] = 0;  // idle since the previous level's reads; used again after the next barrier
+      if (MODE == 2) {
+        // Every thread owns whole 16-byte pieces of the bitmaps: claimed -> visited, claimed cleared, and the
+        // set bits enumerated into the queue -- no atomics on the bitmaps, one counter atomic per piece.
+        if (level == 1 && seed_ok && tid == (((unsigned)s >> 7) & (GEO_THREADS - 1))) {
+          // the seed joins the visited set now; if no self edge re-won it, its distance stays 0
+          // (a re-won seed holds its key until it is resolved with the other level-1 points)
+          if (ld_cg_u32(rowu + s) == GEO_UNVISITED) row[s] = 0.f;
+          vis[(unsigned)s >> 5] |= 1u << (s & 31);
+        }
+        uint4 *clm4 = reinterpret_cast<uint4 *>(clm), *vis4 = reinterpret_cast<uint4 *>(vis);
+        const int n4 = a.bitmap_words >> 2;  // bitmap_words is a multiple of 4
+        for (int i = tid; i < n4; i += GEO_THREADS) {
+          const uint4 c = clm4[i];
+          if ((c.x | c.y | c.z | c.w) == 0u) continue;
+          clm4[i] = make_uint4(0u, 0u, 0u, 0u);
+          uint4 v = vis4[i];
+          v.x |= c.x, v.y |= c.y, v.z |= c.z, v.w |= c.w;
+          vis4[i] = v;
+          int at = atomicAdd(&s_next_n[level & 1], __popc(c.x) + __popc(c.y) + __popc(c.z) + __popc(c.w));
+          const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            for (uint32_t m = cw[w]; m; m &= m - 1) frontier_put(nq, ovf, at++, level & 1, N, i * 128 + w * 32 + __ffs(m) - 1);
+        }
+        __syncthreads();
+      }
       const int nextF = s_next_n[level & 1];
-      if (tid == 0) s_next_n[(level + 1) & 1] = 0;  // idle since the previous level's reads; used again after the barrier below
-      if (BITMAP) {
+      if (MODE == 1) {
         for (int i = tid; i < nextF; i += GEO_THREADS) {
           const int t = frontier_at(nq, i, level);
           atomicOr(vis + ((unsigned)t >> 5), 1u << (t & 31));
-          if (MODE == 2) atomicAnd(clm + ((unsigned)t >> 5), ~(1u << (t & 31)));
         }
       }
-      {
-        const int batch = (int)ngroups * GEO_UNROLL;
-        const int padded = ((nextF + batch - 1) / batch) * batch;
-        for (int i = nextF + (int)tid; i < padded && i < GEO_QCAP; i += GEO_THREADS) nq[i] = N;
-      }
-      if (tid == 0 && level == 1) {
-        // the seed joins the visited set now; if no self edge re-won it, its distance stays 0
-        // (a re-won seed holds its key until it is resolved with the other level-1 points)
+      if (MODE != 2 && tid == 0 && level == 1) {
         if (ld_cg_u32(rowu + s) == GEO_UNVISITED) row[s] = 0.f;
         if (BITMAP) atomicOr(vis + ((unsigned)s >> 5), 1u << (s & 31));
       }
@@ -280,7 +306,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
       int *tq = fq;
       fq = nq;
       nq = tq;
-      __syncthreads();
+      if (MODE != 2) __syncthreads();
     }
     // the points won at the last executed level still hold their keys
     if (level >= 1) {
@@ -290,6 +316,14 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
       }
     }
     if (level == 0 && seed_ok && tid == 0) row[s] = 0.f;  // max_step <= 0: only the seed entry (:118)
+#ifdef GF_TRACE
+    __syncthreads();
+    if (tid == 0 && q < 1024) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t1));
+      a.trace[q * 4 + 0] = tr_t0, a.trace[q * 4 + 1] = tr_t1;
+      a.trace[q * 4 + 2] = (long long)(reached_total - tr_r0), a.trace[q * 4 + 3] = ((long long)blockIdx.x << 32) | level;
+    }
+#endif
   }
   if (tid == 0) {
     if (reached_total) atomicAdd(a.stats, reached_total);
@@ -316,7 +350,7 @@ struct GeoPlan {
 // shared-memory plan, identical for sizing and launching: 227 KB usable per CTA and per SM on sm_100
 static void geo_smem_plan(int N, int *bitmap_words, size_t *smem, int *ctas_per_sm, int *mode) {
   const size_t fixed = sizeof(int) * 2 * GEO_QCAP;
-  const int words = (N + 1 + 31) / 32;  // + the sentinel point N
+  const int words = ((N + 1 + 127) / 128) * 4;  // + the sentinel point N; whole 16-byte pieces
   static int max_mode = -1;
   if (max_mode < 0) {
     const char *e = getenv("GF_GEO_NOBITMAP");  // test knob: 1 = no on-chip state, 2 = visited bitmap only
@@ -411,8 +445,8 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
   ga.bitmap_words = p.bitmap_words;
 #ifdef GF_TRACE
   static long long *d_trace = nullptr;
-  if (!d_trace) cudaMalloc(&d_trace, 8 * 4 * 300);
-  cudaMemsetAsync(d_trace, 0, 8 * 4 * 300, st);
+  if (!d_trace) cudaMalloc(&d_trace, 8 * 4 * 1024);
+  cudaMemsetAsync(d_trace, 0, 8 * 4 * 1024, st);
   ga.trace = d_trace;
 #endif
 #define GF_GEO_LAUNCH(M)                                                                                      \
@@ -433,12 +467,15 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
   {
     static int calls = 0;
     if (++calls == 3) {
-      long long h[4 * 300];
+      static long long h[4 * 1024];
       cudaStreamSynchronize(st);
       cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
-      for (int l = 1; l < 300 && h[l * 4]; ++l)
-        fprintf(stderr, "TRACE level %3d F=%6lld next=%6lld level_us=%7.2f\n", l, h[l * 4 + 3] >> 32,
-                h[l * 4 + 3] & 0xffffffffll, (h[l * 4 + 1] - h[l * 4]) * 1e-3);
+      long long t0 = h[0];
+      for (int q = 0; q < Q && q < 1024; ++q) t0 = h[q * 4] < t0 ? h[q * 4] : t0;
+      for (int q = 0; q < Q && q < 1024; ++q)
+        fprintf(stderr, "TRACE seed %4d cta %3lld start_us=%8.2f dur_us=%8.2f reached=%7lld levels=%3lld\n", q,
+                h[q * 4 + 3] >> 32, (h[q * 4] - t0) * 1e-3, (h[q * 4 + 1] - h[q * 4]) * 1e-3, h[q * 4 + 2],
+                h[q * 4 + 3] & 0xffffffffll);
     }
   }
 #endif
