@@ -38,7 +38,6 @@
 
 namespace gf {
 
-constexpr int GEO_THREADS = 1024;
 constexpr int GEO_QCAP = 4096;  // frontier entries kept in shared memory (per buffer)
 constexpr int GEO_UNROLL = 2;  // frontier points in flight per lane group (x 4 edges per lane)
 constexpr uint32_t GEO_UNVISITED = 0xBF800000u;  // bits of -1.0f
@@ -133,11 +132,21 @@ __device__ __forceinline__ void geo_claim(uint32_t key, int t, int N, int level,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoArgs a) {
+__device__ __forceinline__ void geo_claim4(uint32_t key, const int4 t, int N, int level, uint32_t *vis, uint32_t *clm,
+                                           uint32_t *rowu, int *nq, int *ovf, int *s_next_n) {
+  geo_claim<MODE>(key + 0, t.x, N, level, vis, clm, rowu, nq, ovf, s_next_n);
+  geo_claim<MODE>(key + 1, t.y, N, level, vis, clm, rowu, nq, ovf, s_next_n);
+  geo_claim<MODE>(key + 2, t.z, N, level, vis, clm, rowu, nq, ovf, s_next_n);
+  geo_claim<MODE>(key + 3, t.w, N, level, vis, clm, rowu, nq, ovf, s_next_n);
+}
+
+template <int MODE, int GEO_THREADS>
+__global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_kernel(const GeoArgs a) {
   constexpr bool BITMAP = MODE >= 1;  // a visited bitmap lives in shared memory
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int *q0 = reinterpret_cast<int *>(smem_raw);
-  int *q1 = q0 + GEO_QCAP;
+  // MODE 2 writes the next frontier only after the level's barrier, so one queue serves both
+  int *q1 = MODE == 2 ? q0 : q0 + GEO_QCAP;
   uint32_t *vis = reinterpret_cast<uint32_t *>(q1 + GEO_QCAP);
   uint32_t *clm = vis + a.bitmap_words;
   __shared__ int s_next_n[2], s_seed_q;  // next-frontier counter, by level parity
@@ -238,20 +247,14 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
 #pragma unroll
         for (int u = 0; u < GEO_UNROLL; ++u) {
           const uint32_t key = keybase | (pl[u] << 2);
-          geo_claim<MODE>(key + 0, t[u].x, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
-          geo_claim<MODE>(key + 1, t[u].y, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
-          geo_claim<MODE>(key + 2, t[u].z, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
-          geo_claim<MODE>(key + 3, t[u].w, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+          geo_claim4<MODE>(key, t[u], N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
         }
       }
       for (int node = GEO_QCAP + (int)group; node < F; node += (int)ngroups) {  // spilled tail (rare)
         const unsigned pl = (unsigned)ovf[ovf_index(node, (level - 1) & 1, N)] << lsb;
         const int4 t = __ldg(trow + pl);
         const uint32_t key = keybase | (pl << 2);
-        geo_claim<MODE>(key + 0, t.x, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
-        geo_claim<MODE>(key + 1, t.y, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
-        geo_claim<MODE>(key + 2, t.z, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
-        geo_claim<MODE>(key + 3, t.w, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
+        geo_claim4<MODE>(key, t, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
       }
       if (BITMAP && level > 1) {  // finish the resolve of the points won at level-1
         if (rt >= 0) resolve_finish(rt, rkey, level - 1);
@@ -281,11 +284,18 @@ __global__ void __launch_bounds__(GEO_THREADS, 2) geo_seed_bfs_kernel(const GeoA
           uint4 v = vis4[i];
           v.x |= c.x, v.y |= c.y, v.z |= c.z, v.w |= c.w;
           vis4[i] = v;
-          int at = atomicAdd(&s_next_n[level & 1], __popc(c.x) + __popc(c.y) + __popc(c.z) + __popc(c.w));
-          const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-          for (int w = 0; w < 4; ++w)
-            for (uint32_t m = cw[w]; m; m &= m - 1) frontier_put(nq, ovf, at++, level & 1, N, i * 128 + w * 32 + __ffs(m) - 1);
+          const int cnt = __popc(c.x) + __popc(c.y) + __popc(c.z) + __popc(c.w);
+          int at = atomicAdd(&s_next_n[level & 1], cnt);
+          const unsigned long long lo = ((unsigned long long)c.y << 32) | c.x, hi = ((unsigned long long)c.w << 32) | c.z;
+          if (at + cnt <= GEO_QCAP) {  // the usual case: the whole piece lands in the on-chip queue
+            for (unsigned long long m = lo; m; m &= m - 1) nq[at++] = i * 128 + __ffsll((long long)m) - 1;
+            for (unsigned long long m = hi; m; m &= m - 1) nq[at++] = i * 128 + 64 + __ffsll((long long)m) - 1;
+          } else {
+            for (unsigned long long m = lo; m; m &= m - 1)
+              frontier_put(nq, ovf, at++, level & 1, N, i * 128 + __ffsll((long long)m) - 1);
+            for (unsigned long long m = hi; m; m &= m - 1)
+              frontier_put(nq, ovf, at++, level & 1, N, i * 128 + 64 + __ffsll((long long)m) - 1);
+          }
         }
         __syncthreads();
       }
@@ -343,38 +353,47 @@ static int geo_slot_bits(int k) {
 }
 
 struct GeoPlan {
-  int grid, bitmap_words, mode;
+  int grid, bitmap_words, mode, threads;
   size_t smem;
 };
 
-// shared-memory plan, identical for sizing and launching: 227 KB usable per CTA and per SM on sm_100
-static void geo_smem_plan(int N, int *bitmap_words, size_t *smem, int *ctas_per_sm, int *mode) {
-  const size_t fixed = sizeof(int) * 2 * GEO_QCAP;
+// shared-memory plan, identical for sizing and launching: 227 KB usable per SM on sm_100 (1 KB reserved per CTA)
+static void geo_smem_plan(int N, GeoPlan *p, int *ctas_per_sm) {
   const int words = ((N + 1 + 127) / 128) * 4;  // + the sentinel point N; whole 16-byte pieces
-  static int max_mode = -1;
+  static int max_mode = -1, force_threads = 0;
   if (max_mode < 0) {
     const char *e = getenv("GF_GEO_NOBITMAP");  // test knob: 1 = no on-chip state, 2 = visited bitmap only
     const int v = e ? atoi(e) : 0;
+    const char *t = getenv("GF_GEO_THREADS");  // experiment knob: 512 or 1024
+    force_threads = t ? atoi(t) : 0;
     max_mode = v == 1 ? 0 : (v == 2 ? 1 : 2);
   }
   int m = max_mode;
+  auto bytes_of = [&](int mode) {
+    return sizeof(int) * (size_t)(mode == 2 ? 1 : 2) * GEO_QCAP + sizeof(uint32_t) * (size_t)mode * words;
+  };
   // both bitmaps must fit for mode 2; otherwise mode 0 (two CTAs per SM) measured slightly faster at 1 M
   // points than mode 1 (157 KB of shared memory: one CTA per SM), which stays available through the knob
-  if (m == 2 && fixed + sizeof(uint32_t) * 2 * (size_t)words > (size_t)226 * 1024) m = 0;
-  if (m == 1 && fixed + sizeof(uint32_t) * (size_t)words > (size_t)226 * 1024) m = 0;
-  const size_t bytes = fixed + sizeof(uint32_t) * (size_t)m * words;
-  int per_sm = (int)((size_t)(227 * 1024) / (bytes + 1024));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2) per_sm = 2;  // __launch_bounds__(GEO_THREADS, 2)
-  *bitmap_words = m > 0 ? words : 0;
-  *smem = bytes;
-  *ctas_per_sm = per_sm;
-  *mode = m;
+  if (m == 2 && bytes_of(2) > (size_t)226 * 1024) m = 0;
+  if (m == 1 && bytes_of(1) > (size_t)226 * 1024) m = 0;
+  const size_t bytes = bytes_of(m);
+  int fit = (int)((size_t)(227 * 1024) / (bytes + 1024));
+  if (fit < 1) fit = 1;
+  // 1024-thread CTAs, two per SM.  (Four 512-thread CTAs per SM were measured at c2: +3 % throughput with
+  // four scenes in flight, -8 % for a scene alone, -25 % at c4 -- kept behind GF_GEO_THREADS=512.)
+  int threads = 1024;
+  if (force_threads == 512 || force_threads == 1024) threads = force_threads;
+  const int cap = 2048 / threads;
+  p->bitmap_words = m > 0 ? words : 0;
+  p->smem = bytes;
+  p->mode = m;
+  p->threads = threads;
+  *ctas_per_sm = fit < cap ? fit : cap;
 }
 
 static int plan_geo(int N, int Q, GeoPlan *p) {
   int per_sm = 1;
-  geo_smem_plan(N, &p->bitmap_words, &p->smem, &per_sm, &p->mode);
+  geo_smem_plan(N, p, &per_sm);
   static int bps_cap = -1;
   if (bps_cap < 0) {
     const char *e = getenv("GF_GEO_BPS");  // experiment knob
@@ -388,9 +407,9 @@ static int plan_geo(int N, int Q, GeoPlan *p) {
 }
 
 size_t geodesic_workspace_bytes(int N, int k, int Q) {
-  int words = 0, per_sm = 1, mode = 0;
-  size_t smem = 0;
-  geo_smem_plan(N, &words, &smem, &per_sm, &mode);
+  int per_sm = 1;
+  GeoPlan pl;
+  geo_smem_plan(N, &pl, &per_sm);
   long long grid = (long long)num_sms() * per_sm;
   if (grid > Q) grid = Q;
   if (grid < 1) grid = 1;
@@ -449,18 +468,24 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
   cudaMemsetAsync(d_trace, 0, 8 * 4 * 1024, st);
   ga.trace = d_trace;
 #endif
-#define GF_GEO_LAUNCH(M)                                                                                      \
+#define GF_GEO_LAUNCH(M, T)                                                                                   \
   do {                                                                                                        \
-    GF_CUDA(cudaFuncSetAttribute(geo_seed_bfs_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+    GF_CUDA(cudaFuncSetAttribute(geo_seed_bfs_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                  (int)p.smem));                                                               \
-    geo_seed_bfs_kernel<M><<<p.grid, GEO_THREADS, p.smem, st>>>(ga);                                          \
+    geo_seed_bfs_kernel<M, T><<<p.grid, T, p.smem, st>>>(ga);                                                 \
   } while (0)
-  if (p.mode == 2)
-    GF_GEO_LAUNCH(2);
+  if (p.mode == 2 && p.threads == 512)
+    GF_GEO_LAUNCH(2, 512);
+  else if (p.mode == 2)
+    GF_GEO_LAUNCH(2, 1024);
+  else if (p.mode == 1 && p.threads == 512)
+    GF_GEO_LAUNCH(1, 512);
   else if (p.mode == 1)
-    GF_GEO_LAUNCH(1);
+    GF_GEO_LAUNCH(1, 1024);
+  else if (p.threads == 512)
+    GF_GEO_LAUNCH(0, 512);
   else
-    GF_GEO_LAUNCH(0);
+    GF_GEO_LAUNCH(0, 1024);
 #undef GF_GEO_LAUNCH
   GF_LAUNCHED();
 #ifdef GF_TRACE
