@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--max-step", type=int, default=None, help="override the workload's level bound")
     ap.add_argument("--streams", type=int, default=4,
                     help="scenes in flight on the device (CUDA streams alternated step by step); 1 = strictly serial")
+    ap.add_argument("--seed-sharded", default=None, choices=["nccl", "fused"],
+                    help="ONE scene split by seed blocks over the ranks (SURVEY 8(e), strong scaling): row blocks "
+                         "exchanged by an NCCL all-gather, or stored into the peers by the propagation kernel itself")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -229,6 +232,76 @@ def config_block(cfg, args, extra=None):
 
 
 # ------------------------------------------------------------------------------------------------
+def run_seed_sharded(args):
+    """One scene, seed blocks per rank (strong scaling).  Not the driver's default line: an extra mode
+    for the c4 row of SURVEY 8(e); prints the same JSON shape."""
+    import torch
+    import torch.distributed as dist
+
+    from geoformer_b200 import _capi as C
+    from geoformer_b200.parallel import SeedShardedRows, seed_sharded_guidance, seed_sharded_guidance_fused
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    cfg = workload(args)
+    N, Q, k = cfg["n"], cfg["Q"], cfg["k"]
+    x = make_scene(cfg, 0).to(dev)
+    rows = SeedShardedRows(Q, N) if args.seed_sharded == "fused" else None
+
+    def step():
+        if rows is not None:
+            return seed_sharded_guidance_fused(x, Q, k, cfg["radius"], cfg["max_step"], rows)
+        return seed_sharded_guidance(x, Q, k, cfg["radius"], cfg["max_step"])
+
+    for _ in range(max(3, args.warmup)):
+        out = step()
+    torch.cuda.synchronize(dev)
+    checksum = float(out[1].double().sum().item())
+    K = min(args.steps, 32)
+    sampler = ClockSampler(local)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler.start()
+    C.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    launches = C.launch_count()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / K
+    cs = torch.tensor([checksum], device=dev, dtype=torch.float64)
+    lo, hi = cs.clone(), cs.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "geodesic maps/sec", "value": Q / (ms_step * 1e-3), "unit": "maps/s", "n_gpus": world, "steps": K,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_block(cfg, args, extra={
+                "parallelism": "seed-sharded x%d, exchange: %s" % (world, args.seed_sharded),
+                "l2": "result matrix %.0f MB per rank (> 126 MB L2)" % (4.0 * Q * N / 1e6)}),
+            "gpu_launches": launches, "clocks": clocks,
+            "result_identical_on_all_ranks": bool(lo.item() == hi.item()), "checksum": checksum,
+        }), flush=True)
+    if rows is not None:
+        rows.close()
+    dist.destroy_process_group()
+    return 0
+
+
 def run_ours(args):
     import torch
 
@@ -458,4 +531,6 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse_args()
-    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))
+    if a.impl == "reference":
+        sys.exit(run_reference(a))
+    sys.exit(run_seed_sharded(a) if a.seed_sharded else run_ours(a))

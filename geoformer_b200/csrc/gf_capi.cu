@@ -75,3 +75,33 @@ extern "C" float gf_event_elapsed_ms(void *a, void *b) {
   }
   return ms;
 }
+
+// ---- peer-visible memory (seed-sharded scenes, include/geoformer_b200.h) ---------------------------
+extern "C" int gf_peer_alloc(void **dev_ptr, size_t bytes) {
+  GF_CHECK_ARG(dev_ptr && bytes > 0, "peer_alloc: null pointer or empty allocation");
+  GF_CUDA(cudaMalloc(dev_ptr, bytes));
+  return GF_OK;
+}
+extern "C" int gf_peer_free(void *dev_ptr) {
+  if (dev_ptr) GF_CUDA(cudaFree(dev_ptr));
+  return GF_OK;
+}
+extern "C" int gf_peer_export(void *dev_ptr, void *handle_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == GF_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+  GF_CHECK_ARG(dev_ptr && handle_out, "peer_export: null pointer");
+  cudaIpcMemHandle_t h;
+  GF_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle_out, &h, sizeof(h));
+  return GF_OK;
+}
+extern "C" int gf_peer_open(const void *handle, void **dev_ptr) {
+  GF_CHECK_ARG(handle && dev_ptr, "peer_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  GF_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return GF_OK;
+}
+extern "C" int gf_peer_close(void *dev_ptr) {
+  if (dev_ptr) GF_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return GF_OK;
+}

@@ -40,6 +40,7 @@ namespace gf {
 
 constexpr int GEO_QCAP = 4096;  // frontier entries kept in shared memory (per buffer)
 constexpr int GEO_UNROLL = 2;  // frontier points in flight per lane group (x 4 edges per lane)
+constexpr int GEO_MAX_PEERS = 15;
 constexpr uint32_t GEO_UNVISITED = 0xBF800000u;  // bits of -1.0f
 constexpr uint32_t GEO_KEYBIT = 0x80000000u;
 constexpr uint32_t GEO_KEYMAX = 0x3F800000u;  // row-claim keys must stay below "unvisited"
@@ -55,6 +56,9 @@ struct GeoArgs {
   unsigned *seed_counter;     // work distribution
   unsigned long long *stats;  // [0] reached pairs, [1] deepest level (atomicMax)
   int bitmap_words;           // shared-memory visited bitmap size (0 = test the output row instead)
+  // seed-sharded scenes: finished rows are also stored into the other ranks' matrices (NVLink peer memory)
+  int n_peers;
+  float *peer_geo[GEO_MAX_PEERS];  // row q of this launch goes to peer_geo[r] + q * N
 #ifdef GF_TRACE
   long long *trace;  // development only: per-level timestamps of CTA 0
 #endif
@@ -326,6 +330,25 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
       }
     }
     if (level == 0 && seed_ok && tid == 0) row[s] = 0.f;  // max_step <= 0: only the seed entry (:118)
+    if (a.n_peers > 0) {
+      // The row is final: push it into every peer's matrix now, while other CTAs are still propagating --
+      // the exchange of a seed-sharded scene rides under the compute instead of following it as a
+      // collective.  Same row index on every rank => same 16-byte alignment; stores over NVLink are posted.
+      __syncthreads();
+      const size_t head = ((16 - ((uintptr_t)row & 15)) & 15) / 4;
+      const size_t h = head < (size_t)N ? head : (size_t)N;
+      const size_t nvec = ((size_t)N - h) / 4, tail0 = h + nvec * 4;
+      const float4 *s4 = reinterpret_cast<const float4 *>(row + h);
+      for (size_t i = tid; i < nvec; i += GEO_THREADS) {
+        const float4 v = __ldcg(s4 + i);
+        for (int r = 0; r < a.n_peers; ++r)
+          __stcs(reinterpret_cast<float4 *>(a.peer_geo[r] + (size_t)q * N + h) + i, v);
+      }
+      if ((size_t)tid < h)
+        for (int r = 0; r < a.n_peers; ++r) a.peer_geo[r][(size_t)q * N + tid] = __ldcg(row + tid);
+      if ((size_t)tid < (size_t)N - tail0)
+        for (int r = 0; r < a.n_peers; ++r) a.peer_geo[r][(size_t)q * N + tail0 + tid] = __ldcg(row + tail0 + tid);
+    }
 #ifdef GF_TRACE
     __syncthreads();
     if (tid == 0 && q < 1024) {
@@ -424,7 +447,11 @@ size_t geodesic_workspace_bytes(int N, int k, int Q) {
 
 int geodesic_run(const float *D, const void *I, int is64, int N, int k, const int *seeds, int Q, float radius,
                  int max_step, float *geo, int64_t *stats_out, void *workspace, size_t workspace_bytes,
-                 cudaStream_t st) {
+                 cudaStream_t st, float *const *peer_rows, int n_peers) {
+  if (n_peers < 0 || n_peers > GEO_MAX_PEERS || (n_peers > 0 && !peer_rows)) {
+    set_error("geodesic: %d peers given, at most %d supported", n_peers, GEO_MAX_PEERS);
+    return GF_ERR_INVALID;
+  }
   GeoPlan p;
   int rc = plan_geo(N, Q, &p);
   if (rc) return rc;
@@ -462,6 +489,13 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
   ga.tgt = tgt, ga.len = len, ga.N = N, ga.Q = Q, ga.max_step = max_step, ga.slot_bits = slot_bits;
   ga.seeds = seeds, ga.geo = geo, ga.overflow = overflow, ga.seed_counter = counter, ga.stats = stats;
   ga.bitmap_words = p.bitmap_words;
+  ga.n_peers = n_peers;
+  for (int r = 0; r < GEO_MAX_PEERS; ++r) ga.peer_geo[r] = r < n_peers ? peer_rows[r] : nullptr;
+  for (int r = 0; r < n_peers; ++r)
+    if (!peer_rows[r] || (((uintptr_t)peer_rows[r] ^ (uintptr_t)geo) & 15)) {
+      set_error("geodesic: peer matrix %d is null or not aligned like the local one", r);
+      return GF_ERR_INVALID;
+    }
 #ifdef GF_TRACE
   static long long *d_trace = nullptr;
   if (!d_trace) cudaMalloc(&d_trace, 8 * 4 * 1024);
@@ -526,5 +560,17 @@ extern "C" int gf_geodesic(const float *knn_dist, const void *knn_idx, int idx_i
   if (N == 0 || Q == 0) return GF_OK;
   GF_CHECK_ARG(knn_dist && knn_idx && seeds && geo, "geodesic: null pointer");
   return geodesic_run(knn_dist, knn_idx, idx_is_i64, N, k, seeds, Q, radius, max_step, geo, stats, workspace,
-                      workspace_bytes, (cudaStream_t)stream);
+                      workspace_bytes, (cudaStream_t)stream, nullptr, 0);
+}
+
+extern "C" int gf_geodesic_scatter(const float *knn_dist, const void *knn_idx, int idx_is_i64, int N, int k,
+                                   const int *seeds, int Q, float radius, int max_step, float *geo,
+                                   float *const *peer_geo, int n_peers, int64_t *stats, void *workspace,
+                                   size_t workspace_bytes, void *stream) {
+  GF_CHECK_ARG(N >= 0 && Q >= 0, "geodesic: negative size");
+  GF_CHECK_ARG(k >= 1 && k <= 256, "geodesic: k=%d outside [1,256]", k);
+  if (N == 0 || Q == 0) return GF_OK;
+  GF_CHECK_ARG(knn_dist && knn_idx && seeds && geo, "geodesic: null pointer");
+  return geodesic_run(knn_dist, knn_idx, idx_is_i64, N, k, seeds, Q, radius, max_step, geo, stats, workspace,
+                      workspace_bytes, (cudaStream_t)stream, peer_geo, n_peers);
 }

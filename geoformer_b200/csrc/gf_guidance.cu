@@ -55,7 +55,8 @@ extern "C" size_t gf_guidance_workspace_bytes(int N, int Q, int k) {
 // seeds_given == 0: run FPS (forked stream) and write `seeds`; != 0: `seeds` is an input
 static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, int max_step, int *seeds,
                          int seeds_given, float *geo, float *knn_dist, int32_t *knn_idx32, int64_t *stats,
-                         void *workspace, size_t workspace_bytes, void *stream) {
+                         void *workspace, size_t workspace_bytes, void *stream, float *const *peer_geo = nullptr,
+                         int n_peers = 0) {
   GF_CHECK_ARG(N >= 1 && Q >= 1, "guidance: need N >= 1 and Q >= 1 (N=%d Q=%d)", N, Q);
   GF_CHECK_ARG(k >= 1 && k <= KNN_MAX_K, "guidance: k=%d outside [1,%d]", k, KNN_MAX_K);
   GF_CHECK_ARG(xyz && seeds && geo, "guidance: null pointer");
@@ -99,7 +100,8 @@ static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, in
   // join, then propagate
   if (!seeds_given) GF_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   stage_mark(ST_KNN_DONE, st);
-  return geodesic_run(dist, idx, /*is64=*/0, N, k, seeds, Q, radius, max_step, geo, stats, ws_geo, p.geo, st);
+  return geodesic_run(dist, idx, /*is64=*/0, N, k, seeds, Q, radius, max_step, geo, stats, ws_geo, p.geo, st, peer_geo,
+                      n_peers);
 }
 
 extern "C" int gf_guidance(const float *xyz, int N, int Q, int k, float radius, int max_step, int *seeds, float *geo,
@@ -114,6 +116,13 @@ extern "C" int gf_guidance_seeded(const float *xyz, int N, const int *seeds, int
                                   size_t workspace_bytes, void *stream) {
   return guidance_impl(xyz, N, Q, k, radius, max_step, const_cast<int *>(seeds), 1, geo, knn_dist, knn_idx32, stats,
                        workspace, workspace_bytes, stream);
+}
+
+extern "C" int gf_guidance_seeded_scatter(const float *xyz, int N, const int *seeds, int Q, int k, float radius,
+                                          int max_step, float *geo, float *const *peer_geo, int n_peers,
+                                          int64_t *stats, void *workspace, size_t workspace_bytes, void *stream) {
+  return guidance_impl(xyz, N, Q, k, radius, max_step, const_cast<int *>(seeds), 1, geo, nullptr, nullptr, stats,
+                       workspace, workspace_bytes, stream, peer_geo, n_peers);
 }
 
 extern "C" size_t gf_guidance_host_workspace_bytes(int N, int Q, int k) {

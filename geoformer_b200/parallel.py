@@ -7,7 +7,9 @@ partitionings below are the ones the path itself offers:
                    rank s % world.  NO data-path collective.
   seed-sharded     one large scene: seeds are independent (rows of the output never interact), so
                    each rank propagates a contiguous block of seeds and the (Q/G, N) row blocks are
-                   exchanged with ONE all-gather (NCCL over NVLink).  FPS is inherently sequential
+                   exchanged with ONE all-gather (NCCL over NVLink) -- or, fused (`SeedShardedRows`),
+                   stored by the propagation kernel itself into every peer's matrix over NVLink as
+                   each row finishes, so no collective follows.  FPS is inherently sequential
                    and the kNN graph is needed whole by every rank; both are cheap next to the
                    propagation of a million-point scene, so they are computed redundantly
                    (deterministic => identical on every rank, no broadcast needed).
@@ -56,6 +58,110 @@ def scene_parallel_guidance(scenes, n_queries, neighbor, radius, max_step, rank=
     world = dist.get_world_size() if world is None else world
     fn = guidance_fn or _default_guidance
     return {s: fn(scenes[s], n_queries, neighbor, radius, max_step) for s in shard_scenes(len(scenes), rank, world)}
+
+
+class _DeviceView:
+    """numba-style view of raw device memory, so torch can wrap it without a copy"""
+
+    def __init__(self, address, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(address), False),
+                                         "version": 2, "strides": None}
+
+
+class SeedShardedRows:
+    """The (Q, N) result matrix of a seed-sharded scene, allocated on every rank as peer-visible memory
+    and mapped into every other rank (CUDA IPC over NVLink), so that the propagation kernel of rank r
+    can store its finished rows straight into all of them (`gf_guidance_seeded_scatter`).
+    Set up once per (Q, N) and reused; `close()` unmaps and frees."""
+
+    def __init__(self, n_queries, n_points, group=None, device=None):
+        import ctypes
+
+        from . import _capi as C
+
+        self.group, self.Q, self.N = group, int(n_queries), int(n_points)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        C.require(self.world - 1 <= 15, "seed-sharded scatter supports at most 16 ranks")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        L = C.lib()
+        with torch.cuda.device(self.device):
+            own = ctypes.c_void_p()
+            C.check(L.gf_peer_alloc(ctypes.byref(own), self.Q * self.N * 4), "peer_alloc")
+            self._own = own
+            handle = (ctypes.c_ubyte * 64)()
+            C.check(L.gf_peer_export(own, handle), "peer_export")
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            every = torch.empty((self.world, 64), dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            every = every.cpu()
+            self._mapped = {}
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                h = (ctypes.c_ubyte * 64)(*every[r].tolist())
+                q = ctypes.c_void_p()
+                C.check(L.gf_peer_open(h, ctypes.byref(q)), "peer_open(rank %d)" % r)
+                self._mapped[r] = q
+        self.geo = torch.as_tensor(_DeviceView(own.value, (self.Q, self.N)), device=self.device)
+        self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def row_pointers(self, row0):
+        """(own pointer at row row0, ctypes array of the peers' pointers at the same row)"""
+        import ctypes
+
+        off = int(row0) * self.N * 4
+        peers = [ctypes.c_void_p(p.value + off) for _, p in sorted(self._mapped.items())]
+        return ctypes.c_void_p(self._own.value + off), (ctypes.c_void_p * max(len(peers), 1))(*peers), len(peers)
+
+    def fence(self):
+        """all ranks reach this point of their streams (a one-word all-reduce; orders peer stores and reads)"""
+        dist.all_reduce(self._token, group=self.group)
+
+    def close(self):
+        from . import _capi as C
+
+        L = C.lib()
+        torch.cuda.synchronize(self.device)
+        self.geo = None
+        with torch.cuda.device(self.device):
+            for q in self._mapped.values():
+                L.gf_peer_close(q)
+            self._mapped = {}
+            dist.barrier(group=self.group)  # nobody frees memory a peer still has mapped
+            if self._own is not None:
+                L.gf_peer_free(self._own)
+                self._own = None
+
+
+def seed_sharded_guidance_fused(xyz, n_queries, neighbor, radius, max_step, rows, seeds=None):
+    """One scene split by seed blocks, exchange fused into the propagation kernel.  `rows` is a
+    `SeedShardedRows(n_queries, N)`; returns (seeds, rows.geo) with the full matrix valid on every
+    rank once the stream reaches the end of this call."""
+    import ctypes
+
+    from . import _capi as C
+
+    C.check_cuda_f32(xyz, "xyz")
+    N = xyz.shape[0]
+    C.require(xyz.dim() == 2 and xyz.shape[1] == 3 and N == rows.N and n_queries == rows.Q, "scene / rows mismatch")
+    dev = xyz.device
+    if seeds is None:
+        seeds = _default_fps(xyz, n_queries)
+    C.check_cuda_i32(seeds, "seeds")
+    q0, q1 = shard_seeds(n_queries, rows.rank, rows.world)
+    local = seeds[q0:q1].contiguous()
+    L = C.lib()
+    own, peers, n_peers = rows.row_pointers(q0)
+    rows.fence()  # the peers have finished with the previous contents of their matrices
+    if q1 > q0:
+        with torch.cuda.device(dev):
+            nbytes = L.gf_guidance_workspace_bytes(N, q1 - q0, neighbor)
+            ws = C.workspace.get(dev, "guidance", nbytes)
+            C.check(L.gf_guidance_seeded_scatter(C.ptr(xyz), N, C.ptr(local), q1 - q0, neighbor, float(radius),
+                                                 int(max_step), own, ctypes.cast(peers, ctypes.c_void_p), n_peers,
+                                                 None, C.ptr(ws), nbytes, C.stream_of(dev)), "guidance_seeded_scatter")
+    rows.fence()  # every rank's kernel is complete: all rows have landed everywhere
+    return seeds, rows.geo
 
 
 def seed_sharded_guidance(xyz, n_queries, neighbor, radius, max_step, group=None, fps_fn=None, geodesic_fn=None,

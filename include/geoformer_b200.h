@@ -139,6 +139,29 @@ int gf_guidance_seeded(const float *xyz, int N, const int *seeds, int Q, int k, 
                        float *geo, float *knn_dist, int32_t *knn_idx32, int64_t *stats, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* ---- one scene over several GPUs, split by seed blocks --------------------
+ * New with this library (the reference is single-GPU, train.py:156-185).  Every rank holds the whole
+ * (Q_total,N) matrix; rank r propagates the seeds [row0, row0+Q) and the propagation kernel itself stores
+ * each finished row into the peers' matrices over NVLink while the other seeds are still running, so no
+ * collective follows.  `geo` and every peer_geo[i] point at ROW row0 of the respective matrix (the
+ * addresses of the peers' matrices in this process come from gf_peer_open).  n_peers <= 15.  The
+ * caller separates consecutive calls by a barrier among the ranks (before: peers finished reading
+ * the previous result; after: all rows have landed).                                              */
+int gf_geodesic_scatter(const float *knn_dist, const void *knn_idx, int idx_is_i64, int N, int k, const int *seeds,
+                        int Q, float radius, int max_step, float *geo, float *const *peer_geo, int n_peers,
+                        int64_t *stats, void *workspace, size_t workspace_bytes, void *stream);
+int gf_guidance_seeded_scatter(const float *xyz, int N, const int *seeds, int Q, int k, float radius, int max_step,
+                               float *geo, float *const *peer_geo, int n_peers, int64_t *stats, void *workspace,
+                               size_t workspace_bytes, void *stream);
+/* Peer-visible device memory: a plain cudaMalloc allocation (exportable as a whole), its 64-byte
+ * CUDA IPC handle, and the mapping of another process's handle into this one.                   */
+#define GF_PEER_HANDLE_BYTES 64
+int gf_peer_alloc(void **dev_ptr, size_t bytes);
+int gf_peer_free(void *dev_ptr);
+int gf_peer_export(void *dev_ptr, void *handle_out);
+int gf_peer_open(const void *handle, void **dev_ptr);
+int gf_peer_close(void *dev_ptr);
+
 /* Host-buffer variant (the reference-facing call timed as `e2e`): xyz_host (N,3) in, seeds_host (Q)
  * and geo_host (Q,N) out; copies are issued on `stream` and the call returns after they finish.
  * Device scratch of gf_guidance_host_workspace_bytes() is supplied by the caller.                */

@@ -36,6 +36,18 @@ def _worker(rank, world, port, out_dir):
             ref_seeds, ref_geo = geodesic_guidance(x, Q, 16, 0.5, 24)
             assert torch.equal(seeds, ref_seeds)
             assert geo.shape == (Q, 60_000) and torch.equal(geo, ref_geo)
+        # exchange fused into the propagation kernel (rows stored into the peers' matrices over NVLink)
+        from geoformer_b200.parallel import SeedShardedRows, seed_sharded_guidance_fused
+
+        for n_pts, Q in ((60_000, 64), (30_001, 37), (30_002, world)):  # aligned / unaligned rows, ragged blocks
+            xs = scene(n_pts, 7).to(dev)
+            rows = SeedShardedRows(Q, n_pts)
+            for max_step in (24, 3, 24):  # reuse of the mapped matrices across calls
+                seeds, geo = seed_sharded_guidance_fused(xs, Q, 16, 0.5, max_step, rows)
+                ref_seeds, ref_geo = geodesic_guidance(xs, Q, 16, 0.5, max_step)
+                assert torch.equal(seeds, ref_seeds)
+                assert geo.shape == (Q, n_pts) and torch.equal(geo, ref_geo), (n_pts, Q, max_step)
+            rows.close()
         scenes = [scene(20_000 + 1000 * s, 30 + s).to(dev) for s in range(5)]
         mine = scene_parallel_guidance(scenes, 32, 8, 0.5, 16)
         assert sorted(mine) == shard_scenes(5, rank, world)
