@@ -222,6 +222,16 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
       // bitmaps the visited test reads the row, so the row has to be resolved first.)
       int rt = -1;
       uint32_t rkey = 0;
+      float rw = 0.f, rpd = 0.f;  // edge length and parent distance of this thread's point to resolve
+      bool rissued = false;
+      // second step of the resolve: needs the key (an L2 round trip after the level started), so it is issued
+      // behind the first batch of edge-row loads and completes under the claims
+      auto resolve_issue = [&]() {
+        const unsigned p = (rkey & 0x7fffffffu) >> sb, j = rkey & (KP - 1);
+        rw = __ldg(a.len + ((size_t)p << sb) + j);
+        if (level > 2) rpd = __uint_as_float(ld_cg_u32(rowu + p));
+        rissued = true;
+      };
       if (level > 1) {
         if (BITMAP) {
           if ((int)tid < F) {
@@ -248,6 +258,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
         }
 #pragma unroll
         for (int u = 0; u < GEO_UNROLL; ++u) t[u] = __ldg(trow + pl[u]);
+        if (BITMAP && rt >= 0 && !rissued) resolve_issue();
 #pragma unroll
         for (int u = 0; u < GEO_UNROLL; ++u) {
           const uint32_t key = keybase | (pl[u] << 2);
@@ -261,7 +272,10 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
         geo_claim4<MODE>(key, t, N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
       }
       if (BITMAP && level > 1) {  // finish the resolve of the points won at level-1
-        if (rt >= 0) resolve_finish(rt, rkey, level - 1);
+        if (rt >= 0) {
+          if (!rissued) resolve_issue();
+          row[rt] = level == 2 ? rw : __fadd_rn(rw, rpd);  // :127 / :139,:144
+        }
         for (int i = tid + GEO_THREADS; i < F; i += GEO_THREADS) {
           const int t = frontier_at(fq, i, level - 1);
           resolve_finish(t, ld_cg_u32(rowu + t), level - 1);
