@@ -9,8 +9,15 @@ import torch
 from .. import _capi as C
 
 
+import contextlib
+
+_SAME_DEVICE = contextlib.nullcontext()
+
+
 def _dev(t):
-    return torch.cuda.device(t.device)
+    # a device guard only when the tensor does not live on the current device (the guard costs more
+    # than the launch of the small operators)
+    return _SAME_DEVICE if t.device.index == torch.cuda.current_device() else torch.cuda.device(t.device)
 
 
 def furthest_point_sampling(points, nsamples):

@@ -132,3 +132,68 @@ def test_golden_geodesic_fixtures_on_gpu(dev):
                                      max_step=int(g["max_step"]), neighbor=int(g["k"]), radius=float(g["radius"]),
                                      n_queries=len(g["seeds"]))
         assert np.array_equal(out[0].cpu().numpy(), g["geo"]), path
+
+
+def test_timing_against_reference_kernels(ref_ext, dev):
+    """Same operator, same inputs, same GPU: the reference's own CUDA kernels (oracle/_ref, one CTA per
+    batch element) next to ours, at the shapes GeoFormer calls them with (B=1, N=100k, npoint=2048,
+    radius 0.2, nsample 64).  Results must be identical; the timings are written to
+    gpurun_out/ops_vs_reference.json (copied to profiles/ when refreshed) -- no speed assertion beyond
+    'not slower', the numbers are the evidence."""
+    import json
+    import os
+
+    from geoformer_b200.pointnet2 import _ext
+
+    N, m, ns, r = 100_000, 2048, 64, 0.2
+    xyz = scene(N, 1234)[None].to(dev).contiguous()
+    feats = torch.randn(1, 16, N, generator=torch.Generator().manual_seed(3)).to(dev)
+
+    def timed(fn, reps):
+        out = fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return out, a.elapsed_time(b) / reps
+
+    rows = {}
+
+    def both(name, ref_fn, our_fn, reps=5):
+        ro, rt = timed(ref_fn, reps)
+        oo, ot = timed(our_fn, reps)
+        ro = ro if isinstance(ro, (list, tuple)) else [ro]
+        oo = oo if isinstance(oo, (list, tuple)) else [oo]
+        for x, y in zip(ro, oo):
+            assert torch.equal(x, y), name
+        rows[name] = {"reference_ms": rt, "ours_ms": ot, "speedup": rt / ot}
+        if rt >= 0.1:  # below that both sides measure their host-side launch path, not the kernel
+            assert ot <= rt * 1.05, (name, rt, ot)
+
+    both("furthest_point_sampling N=100k m=256", lambda: ref_ext.furthest_point_sampling(xyz, 256),
+         lambda: _ext.furthest_point_sampling(xyz, 256))
+    both("furthest_point_sampling N=100k m=2048", lambda: ref_ext.furthest_point_sampling(xyz, m),
+         lambda: _ext.furthest_point_sampling(xyz, m), reps=3)
+    inds = _ext.furthest_point_sampling(xyz, m)
+    xyz_t = xyz.transpose(1, 2).contiguous()
+    both("gather_points C=3 m=2048", lambda: ref_ext.gather_points(xyz_t, inds), lambda: _ext.gather_points(xyz_t, inds))
+    new_xyz = _ext.gather_points(xyz_t, inds).transpose(1, 2).contiguous()
+    both("ball_query r=0.2 nsample=64 m=2048", lambda: ref_ext.ball_query(new_xyz, xyz, r, ns),
+         lambda: _ext.ball_query(new_xyz, xyz, r, ns))
+    idx = _ext.ball_query(new_xyz, xyz, r, ns)
+    both("group_points C=16 m=2048 ns=64", lambda: ref_ext.group_points(feats, idx), lambda: _ext.group_points(feats, idx))
+    both("group_points C=3 m=2048 ns=64", lambda: ref_ext.group_points(xyz_t, idx), lambda: _ext.group_points(xyz_t, idx))
+    unknown = xyz[:, :20000].contiguous()
+    both("three_nn n=20000 m=2048", lambda: ref_ext.three_nn(unknown, new_xyz), lambda: _ext.three_nn(unknown, new_xyz))
+    d2, i3 = _ext.three_nn(unknown, new_xyz)
+    w = torch.softmax(-d2, dim=2).contiguous()
+    f2 = torch.randn(1, 32, m, generator=torch.Generator().manual_seed(4)).to(dev)
+    both("three_interpolate C=32 n=20000", lambda: ref_ext.three_interpolate(f2, i3, w),
+         lambda: _ext.three_interpolate(f2, i3, w))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "ops_vs_reference.json"), "w") as f:
+        json.dump({"gpu": torch.cuda.get_device_name(0), "shapes": "B=1 N=100000 npoint=2048 radius=0.2 nsample=64",
+                   "ops": rows}, f, indent=1)
