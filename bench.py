@@ -435,7 +435,7 @@ def run_ours(args):
     # ---- the two distance -> bias epilogues, timed on their own ---------------------
     epilogues = None
     try:
-        from geoformer_b200.bias import decoder_relative_pos, mask_head_relative_coords
+        from geoformer_b200.bias import decoder_relative_embedding, decoder_relative_pos, mask_head_relative_coords
         from geoformer_b200.pointnet2 import _ext as p2
 
         Cn = 2048  # contexts of the real model (geoformer_fs.py:630-645); the seeds are their prefix
@@ -457,10 +457,18 @@ def run_ours(args):
 
         t_dec = timeit(lambda: decoder_relative_pos([geo0], ctx, q_xyz, ctx_xyz))
         t_mask = timeit(lambda: mask_head_relative_coords(geo0, xs[0], q_xyz[0]))
+        gauss_B = torch.randn(3, 32, device=dev)  # d_pos = 64 (config dec_dim), pos_embedding.py:38-41
+        pc = [xs[0].min(0)[0][None].contiguous(), xs[0].max(0)[0][None].contiguous()]
+        t_four = timeit(lambda: decoder_relative_embedding([geo0], ctx, q_xyz, ctx_xyz, gauss_B, pc))
+        b_four = 4.0 * Q * Cn * (1 + 64)          # gather + (B,Q,C,64) write; the (B,Q,C,3) tensor never exists
         b_dec = 4.0 * Q * Cn * (1 + 3)            # gather + (B,Q,C,3) write
         b_mask = 4.0 * Q * N * (1 + 3) + 12.0 * N  # one read of geo + (Q,3,N) write + coords
         epilogues = {
             "decoder_bias": {"ms": t_dec, "algorithmic_bytes": b_dec, "GBps": b_dec / t_dec / 1e6},
+            "decoder_bias_fourier": {"ms": t_four, "algorithmic_bytes": b_four, "GBps": b_four / t_four / 1e6,
+                                     "frac_of_hbm_peak": b_four / t_four / 1e6 / peak,
+                                     "note": "geoformer_fs.py:680-712 fused: gather, fill, normalise, 3x32 projection, "
+                                             "sin|cos, written once as (B,Q,C,64)"},
             "mask_head_bias": {"ms": t_mask, "algorithmic_bytes": b_mask, "GBps": b_mask / t_mask / 1e6,
                                "frac_of_hbm_peak": b_mask / t_mask / 1e6 / peak,
                                "note": "timed through the Python call incl. output allocation; the kernel reads geo "

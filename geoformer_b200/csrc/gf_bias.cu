@@ -20,19 +20,25 @@ __device__ __forceinline__ float block_max(float v, float *sm) {
 }
 
 __global__ void bias_init_kernel(uint32_t *gmax) { *gmax = 0u; }
+// ordered-int maxima: 0 is below every float, so zero is the identity of the atomicMax reductions
+__global__ void bias_zero_kernel(uint32_t *p, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0u;
+}
 
 // ---- decoder epilogue -------------------------------------------------------------------------------
-// rowmax[q] = max_c geo[q, ctx_idx[c]]      (geoformer_fs.py:685-691)
+// rowmax[q] = max_c geo[q, ctx_idx[c]]      (geoformer_fs.py:685-691); several CTAs per row (a row is only
+// C gathers: one CTA per row would be a chain of dependent L2 round trips), combined by an ordered atomicMax
 __global__ void __launch_bounds__(256)
     bias_ctx_rowmax_kernel(const float *__restrict__ geo, int ld, const int *__restrict__ ctx_idx, int C,
-                           float *__restrict__ rowmax, uint32_t *__restrict__ gmax) {
+                           uint32_t *__restrict__ rowmax_ord, uint32_t *__restrict__ gmax) {
   __shared__ float sm[8];
-  const int q = blockIdx.x;
+  const int q = blockIdx.y;
   float v = -__int_as_float(0x7f800000);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) v = fmaxf(v, __ldg(geo + (size_t)q * ld + __ldg(ctx_idx + c)));
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x)
+    v = fmaxf(v, __ldg(geo + (size_t)q * ld + __ldg(ctx_idx + c)));
   float r = block_max(v, sm);
-  if (threadIdx.x == 0) {
-    rowmax[q] = r;
+  if (threadIdx.x == 0 && r > -__int_as_float(0x7f800000)) {
+    atomicMax(rowmax_ord + q, f2ord(r));
     atomicMax(gmax, f2ord(r));  // :692  max over every (batch, query)
   }
 }
@@ -41,12 +47,12 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     bias_ctx_write_kernel(const float *__restrict__ geo, int ld, const int *__restrict__ ctx_idx,
                           const float *__restrict__ query_xyz, const float *__restrict__ ctx_xyz, int Q, int C,
-                          const float *__restrict__ rowmax, const uint32_t *__restrict__ gmax, float *__restrict__ out) {
+                          const uint32_t *__restrict__ rowmax, const uint32_t *__restrict__ gmax, float *__restrict__ out) {
   const float M = ord2f(*gmax);
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Q * C; e += gridDim.x * blockDim.x) {
     const int q = e / C, c = e - q * C;
     float g = __ldg(geo + (size_t)q * ld + __ldg(ctx_idx + c));
-    float m = rowmax[q];
+    float m = ord2f(rowmax[q]);
     if (m < 0.f) m = M;  // :693
     float o0 = g, o1 = g, o2 = g;
     if (g < 0.f) {
@@ -56,6 +62,63 @@ __global__ void __launch_bounds__(256)
     }
     float *o = out + (size_t)e * 3;
     o[0] = o0, o[1] = o1, o[2] = o2;
+  }
+}
+
+// ---- decoder epilogue fused with the Fourier position embedding ------------------
+// What the decoder consumes is not the (B,Q,C,3) tensor above but its embedding
+// (geoformer_fs.py:704-712 -> pos_embedding.py:88-114, utils_pc.py:35-61):
+//   v_a   = the value above, a = 0..2
+//   n_a   = ((v_a - pc_min[b,a]) * 1 / (pc_max[b,a] - pc_min[b,a]) + 0) * 2pi     (shift_scale_points, then *= 2*np.pi)
+//   p_j   = sum_a n_a * gauss_B[a,j]                                               (torch.mm, j < d_out)
+//   out[b,q,c,j] = sin(p_j), out[b,q,c,d_out+j] = cos(p_j)
+// i.e. the memory behind the reference's relative_pos view (Q,C,B,2*d_out).  One warp takes 32 contexts of one
+// query: lane l prepares n_0..2 of context l (gather, fill, normalisation: done once, not once per
+// frequency), then the warp walks the 32 contexts with lane = frequency, so every store is a full 128-byte line.
+__global__ void __launch_bounds__(256)
+    bias_ctx_fourier_kernel(const float *__restrict__ geo, int ld, const int *__restrict__ ctx_idx,
+                            const float *__restrict__ query_xyz, const float *__restrict__ ctx_xyz, int Q, int C,
+                            const uint32_t *__restrict__ rowmax, const uint32_t *__restrict__ gmax,
+                            const float *__restrict__ gauss_B, int d_out, int ldb, const float *__restrict__ pc_min,
+                            const float *__restrict__ pc_max, float *__restrict__ out) {
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int q = blockIdx.y;
+  float m = ord2f(rowmax[q]);
+  if (m < 0.f) m = ord2f(*gmax);  // :693
+  const float qx = query_xyz[q * 3 + 0], qy = query_xyz[q * 3 + 1], qz = query_xyz[q * 3 + 2];
+  const float mn0 = pc_min[0], mn1 = pc_min[1], mn2 = pc_min[2];
+  const float df0 = __fsub_rn(pc_max[0], mn0), df1 = __fsub_rn(pc_max[1], mn1), df2 = __fsub_rn(pc_max[2], mn2);
+  const float two_pi = 6.2831855f;  // float(2 * np.pi)
+  const int d_pos = 2 * d_out;
+  for (int c0 = (blockIdx.x * nwarp + warp) * 32; c0 < C; c0 += gridDim.x * nwarp * 32) {
+    const int c = c0 + (int)lane;
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+    if (c < C) {
+      const float g = __ldg(geo + (size_t)q * ld + __ldg(ctx_idx + c));
+      float v0 = g, v1 = g, v2 = g;
+      if (g < 0.f) {
+        v0 = __fadd_rn(m, fabsf(__fsub_rn(qx, ctx_xyz[c * 3 + 0])));
+        v1 = __fadd_rn(m, fabsf(__fsub_rn(qy, ctx_xyz[c * 3 + 1])));
+        v2 = __fadd_rn(m, fabsf(__fsub_rn(qz, ctx_xyz[c * 3 + 2])));
+      }
+      n0 = __fmul_rn(__fdiv_rn(__fsub_rn(v0, mn0), df0), two_pi);
+      n1 = __fmul_rn(__fdiv_rn(__fsub_rn(v1, mn1), df1), two_pi);
+      n2 = __fmul_rn(__fdiv_rn(__fsub_rn(v2, mn2), df2), two_pi);
+    }
+    const int nc = min(32, C - c0);
+    for (int j = (int)lane; j < d_out; j += 32) {
+      const float b0 = __ldg(gauss_B + j), b1 = __ldg(gauss_B + ldb + j), b2 = __ldg(gauss_B + 2 * ldb + j);
+      float *o = out + ((size_t)q * C + c0) * d_pos + j;
+      for (int i = 0; i < nc; ++i) {
+        const float x0 = __shfl_sync(0xffffffffu, n0, i), x1 = __shfl_sync(0xffffffffu, n1, i),
+                    x2 = __shfl_sync(0xffffffffu, n2, i);
+        const float p = fmaf(x2, b2, fmaf(x1, b1, __fmul_rn(x0, b0)));
+        float sn, cs;
+        sincosf(p, &sn, &cs);
+        __stcs(o + (size_t)i * d_pos, sn);
+        __stcs(o + (size_t)i * d_pos + d_out, cs);
+      }
+    }
   }
 }
 
@@ -159,18 +222,19 @@ extern "C" int gf_bias_decoder(const float *const *geo_ptrs, const int *geo_ld, 
   if ((long long)B * Q * C == 0) return GF_OK;
   GF_CHECK_ARG(geo_ptrs && geo_ld && ctx_idx && query_xyz && ctx_xyz && out, "bias_decoder: null pointer");
   Arena a(workspace, workspace_bytes);
-  float *rowmax = a.take<float>((size_t)B * Q);
-  uint32_t *gmax = a.take<uint32_t>(1);
+  uint32_t *rowmax = a.take<uint32_t>((size_t)B * Q + 1);  // + the global maximum, zeroed together
+  uint32_t *gmax = rowmax + (size_t)B * Q;
   if (!a.ok) {
     set_error("bias_decoder: workspace too small");
     return GF_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  bias_init_kernel<<<1, 1, 0, st>>>(gmax);
+  bias_zero_kernel<<<(B * Q + 256) / 256, 256, 0, st>>>(rowmax, B * Q + 1);
   GF_LAUNCHED();
+  const int rchunks = C >= 1024 ? 4 : 1;
   for (int b = 0; b < B; ++b) {
-    bias_ctx_rowmax_kernel<<<Q, 256, 0, st>>>(geo_ptrs[b], geo_ld[b], ctx_idx + (size_t)b * C, C, rowmax + (size_t)b * Q,
-                                              gmax);
+    bias_ctx_rowmax_kernel<<<dim3(rchunks, Q), 256, 0, st>>>(geo_ptrs[b], geo_ld[b], ctx_idx + (size_t)b * C, C,
+                                                           rowmax + (size_t)b * Q, gmax);
     GF_LAUNCHED();
   }
   for (int b = 0; b < B; ++b) {
@@ -179,6 +243,44 @@ extern "C" int gf_bias_decoder(const float *const *geo_ptrs, const int *geo_ld, 
     bias_ctx_write_kernel<<<grid, 256, 0, st>>>(geo_ptrs[b], geo_ld[b], ctx_idx + (size_t)b * C,
                                                 query_xyz + (size_t)b * Q * 3, ctx_xyz + (size_t)b * C * 3, Q, C,
                                                 rowmax + (size_t)b * Q, gmax, out + (size_t)b * Q * C * 3);
+    GF_LAUNCHED();
+  }
+  return GF_OK;
+}
+
+extern "C" int gf_bias_decoder_fourier(const float *const *geo_ptrs, const int *geo_ld, const int *ctx_idx,
+                                       const float *query_xyz, const float *ctx_xyz, int B, int Q, int C,
+                                       const float *gauss_B, int d_out, int gauss_ld, const float *pc_min,
+                                       const float *pc_max, float *out, void *workspace, size_t workspace_bytes,
+                                       void *stream) {
+  GF_CHECK_ARG(B >= 0 && Q >= 0 && C >= 0, "bias_decoder_fourier: negative size");
+  GF_CHECK_ARG(d_out >= 1 && gauss_ld >= d_out, "bias_decoder_fourier: d_out=%d, gauss_ld=%d", d_out, gauss_ld);
+  if ((long long)B * Q * C == 0) return GF_OK;
+  GF_CHECK_ARG(geo_ptrs && geo_ld && ctx_idx && query_xyz && ctx_xyz && gauss_B && pc_min && pc_max && out,
+               "bias_decoder_fourier: null pointer");
+  Arena a(workspace, workspace_bytes);
+  uint32_t *rowmax = a.take<uint32_t>((size_t)B * Q + 1);  // + the global maximum, zeroed together
+  uint32_t *gmax = rowmax + (size_t)B * Q;
+  if (!a.ok) {
+    set_error("bias_decoder_fourier: workspace too small");
+    return GF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  bias_zero_kernel<<<(B * Q + 256) / 256, 256, 0, st>>>(rowmax, B * Q + 1);
+  GF_LAUNCHED();
+  const int rchunks = C >= 1024 ? 4 : 1;
+  for (int b = 0; b < B; ++b) {
+    bias_ctx_rowmax_kernel<<<dim3(rchunks, Q), 256, 0, st>>>(geo_ptrs[b], geo_ld[b], ctx_idx + (size_t)b * C, C,
+                                                           rowmax + (size_t)b * Q, gmax);
+    GF_LAUNCHED();
+  }
+  for (int b = 0; b < B; ++b) {
+    int gx = (C + 255) / 256;  // 8 warps x 32 contexts per block: one pass per warp, no ragged second round
+    if (gx > 4096) gx = 4096;
+    bias_ctx_fourier_kernel<<<dim3(gx, Q), 256, 0, st>>>(
+        geo_ptrs[b], geo_ld[b], ctx_idx + (size_t)b * C, query_xyz + (size_t)b * Q * 3, ctx_xyz + (size_t)b * C * 3, Q, C,
+        rowmax + (size_t)b * Q, gmax, gauss_B, d_out, gauss_ld, pc_min + (size_t)b * 3, pc_max + (size_t)b * 3,
+        out + (size_t)b * Q * C * 2 * d_out);
     GF_LAUNCHED();
   }
   return GF_OK;

@@ -119,6 +119,16 @@ size_t gf_bias_workspace_bytes(int B, int Q);
 int gf_bias_decoder(const float *const *geo_ptrs, const int *geo_ld, const int *ctx_idx, const float *query_xyz,
                     const float *ctx_xyz, int B, int Q, int C, float *out, void *workspace, size_t workspace_bytes,
                     void *stream);
+/* The same epilogue fused with the Fourier position embedding the decoder actually consumes
+ * (geoformer_fs.py:704-712 -> PositionEmbeddingCoordsSine.get_fourier_embeddings, pos_embedding.py:88-114,
+ * normalize=True -> shift_scale_points, utils_pc.py:35-61): gauss_B (3, >= d_out) f32 with row stride
+ * gauss_ld, pc_min / pc_max (B,3) -> out (B,Q,C,2*d_out) f32 = [sin | cos]; the reference's
+ * relative_embedding_pos is the (Q,C,B,2*d_out) permuted view of exactly this memory.  The (B,Q,C,3)
+ * intermediate is never materialised.  Tolerance 2e-5 absolute (order of the 3-term dot product, sinf). */
+int gf_bias_decoder_fourier(const float *const *geo_ptrs, const int *geo_ld, const int *ctx_idx,
+                            const float *query_xyz, const float *ctx_xyz, int B, int Q, int C, const float *gauss_B,
+                            int d_out, int gauss_ld, const float *pc_min, const float *pc_max, float *out,
+                            void *workspace, size_t workspace_bytes, void *stream);
 /* mask-head relative coordinates (geoformer_fs.py:263-292):
  * geo (Q,N), coords (N,3), seed_xyz (Q,3) -> out (Q,3,N).                                       */
 int gf_bias_mask_head(const float *geo, const float *coords, const float *seed_xyz, int Q, int N, float *out,

@@ -3,6 +3,9 @@
 Plain torch ops on CPU tensors, following the reference line by line:
   decoder_relative_pos      : model/geoformer/geoformer_fs.py:680-702
   mask_head_relative_coords : model/geoformer/geoformer_fs.py:263-289
+  decoder_relative_embedding: model/geoformer/geoformer_fs.py:680-712 with model/pos_embedding.py:88-114 and
+                              util/utils_pc.py:35-61 (pinned by tests/golden/fourier_golden.npz, which was produced
+                              by the reference's own PositionEmbeddingCoordsSine)
 (only float32 add / sub / abs / max / sqrt / sign: every op is correctly rounded, so the CUDA
 kernels are expected to match bit for bit; the tests allow 1e-6 relative as SURVEY 8(c) states).
 """
@@ -23,6 +26,30 @@ def decoder_relative_pos(geo_dists, pre_enc_inds, query_locs, context_locs):
     cond = g < 0
     g[cond] = m[cond] + rel[cond]  # :701-702
     return g
+
+
+def fourier_embedding(xyz, gauss_B, pc_dims, num_channels=None):
+    """PositionEmbeddingCoordsSine.get_fourier_embeddings with normalize=True (pos_embedding.py:88-114) and the
+    shift_scale_points it calls (utils_pc.py:35-61, dst_range = [0, 1]).  xyz (B, n, 3) -> (B, d_pos, n)."""
+    d_out = gauss_B.shape[1] if num_channels is None else num_channels // 2
+    B, n = xyz.shape[0], xyz.shape[1]
+    xyz = xyz.clone()
+    src_min, src_max = pc_dims
+    src_diff = src_max[:, None, :] - src_min[:, None, :]  # utils_pc.py:58
+    dst_diff = torch.ones_like(src_diff) - torch.zeros_like(src_diff)  # :59
+    xyz = (((xyz - src_min[:, None, :]) * dst_diff) / src_diff) + torch.zeros_like(src_diff)  # :60
+    xyz *= 2 * np.pi  # pos_embedding.py:107
+    xyz = xyz.float()
+    proj = torch.mm(xyz.view(-1, 3), gauss_B[:, :d_out]).view(B, n, d_out)  # :109
+    return torch.cat([proj.sin(), proj.cos()], dim=2).permute(0, 2, 1)  # :110-113
+
+
+def decoder_relative_embedding(geo_dists, pre_enc_inds, query_locs, context_locs, gauss_B, pc_dims):
+    """geoformer_fs.py:680-712: relative_embedding_pos, shape (Q, C, B, d_pos)."""
+    g = decoder_relative_pos(geo_dists, pre_enc_inds, query_locs, context_locs)
+    B, Q, Cn = g.shape[:3]
+    e = fourier_embedding(g.reshape(B, Q * Cn, -1), gauss_B, pc_dims).reshape(B, -1, Q, Cn)  # :704-711
+    return e.permute(2, 3, 0, 1)  # :712
 
 
 def mask_head_relative_coords(geo_dist, coords, fps_sampling_coords):

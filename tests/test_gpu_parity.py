@@ -408,6 +408,43 @@ def test_bias_epilogues(oracle_lib, dev):
         assert torch.equal(m, rm)
 
 
+def test_decoder_fourier_embedding(dev):
+    """geoformer_fs.py:680-712 fused (gather -> fill -> normalise -> 3x32 projection -> sin|cos) against the
+    fixture produced by the reference's own PositionEmbeddingCoordsSine, and against the torch restatement
+    at the model's shapes.  Tolerance 2e-5 absolute: the order of the 3-term dot product (torch.mm) and the
+    last ulp of sinf/cosf at arguments of up to ~50 rad."""
+    import os
+
+    from oracle import bias as obias
+
+    from geoformer_b200.bias import decoder_relative_embedding
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fourier_golden.npz"))
+    t = {k: torch.from_numpy(g[k]) for k in g.files}
+    out = decoder_relative_embedding([t["geo0"].to(dev), t["geo1"].to(dev)], t["inds"].to(dev), t["qry"].to(dev),
+                                     t["ctx"].to(dev), t["gauss_B"].to(dev), [t["pc_min"].to(dev), t["pc_max"].to(dev)])
+    assert out.shape == (12, 40, 2, 64) and out.stride() == (40 * 64, 64, 12 * 40 * 64, 1)  # the reference's view
+    torch.testing.assert_close(out.cpu().contiguous(), t["emb"], rtol=0, atol=2e-5)
+    # model shapes: B=1, Q=256 queries, C=2048 contexts, d_pos=64; ragged context count and a narrower embedding too
+    for Q, Cn, d_pos, nch in ((256, 2048, 64, None), (37, 301, 64, None), (16, 100, 96, 64)):
+        gen = torch.Generator().manual_seed(Q)
+        N = 20000
+        geo = torch.rand(Q, N, generator=gen) * 4.0
+        geo[torch.rand(Q, N, generator=gen) < 0.5] = -1.0
+        geo[1] = -1.0
+        x = scene(N, 3)
+        inds = torch.randperm(N, generator=gen)[:Cn].int()[None]
+        ctx = x[inds[0].long()][None].contiguous()
+        qry = ctx[:, :Q].contiguous()
+        gb = torch.randn(3, d_pos // 2, generator=gen)
+        pc = [x.min(0)[0][None].contiguous(), x.max(0)[0][None].contiguous()]
+        ours = decoder_relative_embedding([geo.to(dev)], inds.to(dev), qry.to(dev), ctx.to(dev), gb.to(dev),
+                                          [pc[0].to(dev), pc[1].to(dev)], num_channels=nch).cpu()
+        ref = obias.decoder_relative_embedding([geo], inds, qry, ctx, gb if nch is None else gb[:, : nch // 2], pc)
+        assert ours.shape == ref.shape
+        torch.testing.assert_close(ours.contiguous(), ref.contiguous(), rtol=0, atol=2e-5)
+
+
 # ------------------------------------------------------------------------- python surface / e2e
 def test_group_points_pipeline_and_autograd(oracle_lib, dev):
     """set_aggregator.group_points chain (pointnet2_modules.py:200-226): FPS -> gather -> ball query ->

@@ -163,3 +163,29 @@ def test_oracle_three_nn_interpolate_match_reference_kernel_fixture(oracle_lib, 
     assert np.array_equal(oracle_lib.three_interpolate(g["ti_feats"], idx, g["ti_w"]), g["ti_out"])
     d2s, idxs = oracle_lib.three_nn(g["tnn_unknown"][:, :10], g["tnn_known"][:, :2])
     assert np.array_equal(idxs, g["tnn_small_idx"]) and np.array_equal(d2s, g["tnn_small_d2"])
+
+
+# ---- decoder relative-position embedding (geoformer_fs.py:680-712) ----------------------------------
+# fixture = the reference's own PositionEmbeddingCoordsSine applied on CPU (tests/golden/make_golden_fourier.py)
+def _fourier_fixture():
+    import torch
+
+    g = np.load(os.path.join(GOLD, "fourier_golden.npz"))
+    t = {k: torch.from_numpy(g[k]) for k in g.files}
+    return t
+
+
+def test_oracle_fourier_embedding_matches_reference_module_fixture():
+    import torch
+
+    from oracle import bias as obias
+
+    t = _fourier_fixture()
+    emb = obias.decoder_relative_embedding([t["geo0"], t["geo1"]], t["inds"], t["qry"], t["ctx"], t["gauss_B"],
+                                           [t["pc_min"], t["pc_max"]])
+    assert emb.shape == t["emb"].shape == (12, 40, 2, 64)
+    # same torch ops on the same platform class (CPU); allow the last ulps of sin/cos across torch builds
+    torch.testing.assert_close(emb.contiguous(), t["emb"], rtol=0, atol=2e-6)
+    # the [sin | cos] halves are consistent
+    s, c = emb[..., :32], emb[..., 32:]
+    torch.testing.assert_close(s * s + c * c, torch.ones_like(s), rtol=0, atol=1e-5)
