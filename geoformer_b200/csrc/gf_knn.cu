@@ -329,7 +329,18 @@ __global__ void __launch_bounds__(128)
           }
           if (xa > xb) continue;
           const int p0 = __ldg(start + rowbase + xa), p1 = __ldg(start + rowbase + xb + 1);
-          for (int p = p0; p < p1; ++p) {
+          int p = p0;
+          for (; p + 4 <= p1; p += 4) {  // four candidates in flight: the loads and distances overlap the offers
+            const float4 c0 = __ldg(sorted + p), c1 = __ldg(sorted + p + 1), c2 = __ldg(sorted + p + 2),
+                         c3 = __ldg(sorted + p + 3);
+            const float e0 = sq3(c0.x - qx, c0.y - qy, c0.z - qz), e1 = sq3(c1.x - qx, c1.y - qy, c1.z - qz),
+                        e2 = sq3(c2.x - qx, c2.y - qy, c2.z - qz), e3 = sq3(c3.x - qx, c3.y - qy, c3.z - qz);
+            top.offer(e0, __float_as_int(c0.w));
+            top.offer(e1, __float_as_int(c1.w));
+            top.offer(e2, __float_as_int(c2.w));
+            top.offer(e3, __float_as_int(c3.w));
+          }
+          for (; p < p1; ++p) {
             float4 c = __ldg(sorted + p);
             float d2 = sq3(c.x - qx, c.y - qy, c.z - qz);
             top.offer(d2, __float_as_int(c.w));
