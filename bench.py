@@ -481,7 +481,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         pinned = [x.pin_memory() for x in scenes_host]
-        nthreads = 3
+        nthreads = 4
         hgs = [HostGuidance(N, Q, k, cfg["radius"], cfg["max_step"], device=dev) for _ in range(nthreads)]
         Ke = max(4, min(K, 32))
         for h in hgs:
@@ -505,7 +505,25 @@ def run_ours(args):
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # what the link alone gives: the same 102 MB of maps copied device -> pinned host, nothing else running
+        link = None
+        try:
+            src = torch.empty((Q, N), dtype=torch.float32, device=dev)
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            hgs[0].geo_host.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            a_.record()
+            for _ in range(4):
+                hgs[0].geo_host.copy_(src, non_blocking=True)
+            b_.record()
+            torch.cuda.synchronize(dev)
+            link = 4.0 * Q * N * 4 / (a_.elapsed_time(b_) * 1e-3) / 1e9
+            del src
+        except Exception:
+            pass
         e2e = {"value": world * Ke * Q / dt, "unit": "maps/s", "h2d_bytes_per_step": hgs[0].h2d_bytes,
+               "d2h_link_GBps": link,
+               "d2h_achieved_GBps": hgs[0].d2h_bytes * Ke / dt / 1e9,
                "d2h_bytes_per_step": hgs[0].d2h_bytes, "steps": Ke, "ms_per_step": 1e3 * dt / Ke,
                "call": "gf_guidance_host (pinned host buffers, %d overlapped host threads)" % nthreads}
 
