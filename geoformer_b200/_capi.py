@@ -42,15 +42,15 @@ SIGNATURES = {
     "gf_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gf_knn": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "gf_geodesic_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "gf_geodesic": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
+    "gf_geodesic": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "gf_bias_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gf_bias_decoder": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "gf_bias_decoder_fourier": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P,
                                         c_size_t, _P]),
-    "gf_bias_mask_head": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, c_size_t, _P]),
+    "gf_bias_mask_head": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "gf_guidance_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "gf_guidance": (c_int, [_P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "gf_guidance_seeded": (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gf_guidance": (c_int, [_P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gf_guidance_seeded": (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gf_geodesic_scatter": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_int, _P, _P, c_int, _P, _P,
                                     c_size_t, _P]),
     "gf_guidance_seeded_scatter": (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, c_int, _P, _P,

@@ -76,20 +76,26 @@ def decoder_relative_embedding(geo_dists, pre_enc_inds, query_locs, context_locs
     return out.permute(1, 2, 0, 3)
 
 
-def mask_head_relative_coords(geo_dist, coords, fps_sampling_coords):
+def mask_head_relative_coords(geo_dist, coords, fps_sampling_coords, row_max=None):
     """geo_dist (Q,N), coords (N,3), fps_sampling_coords (Q,3) -> (Q,3,N): seed - point, pushed
-    outwards by sqrt(rowmax) along each axis where the point is unreachable from the seed."""
+    outwards by sqrt(rowmax) along each axis where the point is unreachable from the seed.
+    row_max: optional (Q,) row maxima as produced by the propagation (`geodesic_guidance(..., row_max=t)`);
+    with it the maps are read once instead of twice."""
     C.check_cuda_f32(geo_dist, "geo_dist")
     C.check_cuda_f32(coords, "coords")
     C.check_cuda_f32(fps_sampling_coords, "fps_sampling_coords")
     Q, N = geo_dist.shape
     C.require(tuple(coords.shape) == (N, 3) and tuple(fps_sampling_coords.shape) == (Q, 3), "shape mismatch")
+    if row_max is not None:
+        C.check_cuda_f32(row_max, "row_max")
+        C.require(tuple(row_max.shape) == (Q,), "row_max must be (Q,)")
     dev = geo_dist.device
     out = torch.empty((Q, 3, N), dtype=torch.float32, device=dev)
     L = C.lib()
     with torch.cuda.device(dev):
         nbytes = L.gf_bias_workspace_bytes(1, max(Q, 1))
         ws = C.workspace.get(dev, "bias", nbytes)
-        C.check(L.gf_bias_mask_head(C.ptr(geo_dist), C.ptr(coords), C.ptr(fps_sampling_coords), Q, N, C.ptr(out),
+        C.check(L.gf_bias_mask_head(C.ptr(geo_dist), C.ptr(coords), C.ptr(fps_sampling_coords), Q, N, C.ptr(row_max),
+                                    C.ptr(out),
                                     C.ptr(ws), nbytes, C.stream_of(dev)), "bias_mask_head")
     return out

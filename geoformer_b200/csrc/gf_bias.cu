@@ -160,6 +160,22 @@ __device__ __forceinline__ float mask_push(float d, float s, bool unreached) {
   return __fadd_rn(d, __fmul_rn(s, sg));
 }
 
+// row maxima handed over by the producer of the maps (gf_geodesic / gf_guidance `row_max`): no pass over geo.
+// One block: it also initialises the global maximum, so nothing has to be zeroed beforehand.
+__global__ void __launch_bounds__(1024)
+    bias_rowmax_import_kernel(const float *__restrict__ row_max, int Q, uint32_t *__restrict__ rowmax_ord,
+                              uint32_t *__restrict__ gmax) {
+  __shared__ float sm[32];
+  float v = -__int_as_float(0x7f800000);
+  for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+    const float r = row_max[q];
+    rowmax_ord[q] = f2ord(r);
+    v = fmaxf(v, r);
+  }
+  const float r = block_max(v, sm);
+  if (threadIdx.x == 0) *gmax = r > -__int_as_float(0x7f800000) ? f2ord(r) : 0u;
+}
+
 // out[q,a,p] = d + (geo[q,p] < 0 ? sqrt(m_q) * sign(d) : 0),  d = seed_xyz[q,a] - coords[p,a]   (:271-289)
 template <bool VEC>
 __global__ void __launch_bounds__(256)
@@ -287,7 +303,8 @@ extern "C" int gf_bias_decoder_fourier(const float *const *geo_ptrs, const int *
 }
 
 extern "C" int gf_bias_mask_head(const float *geo, const float *coords, const float *seed_xyz, int Q, int N,
-                                 float *out, void *workspace, size_t workspace_bytes, void *stream) {
+                                 const float *row_max, float *out, void *workspace, size_t workspace_bytes,
+                                 void *stream) {
   GF_CHECK_ARG(Q >= 0 && N >= 0, "bias_mask_head: negative size");
   if ((long long)Q * N == 0) return GF_OK;
   GF_CHECK_ARG(geo && coords && seed_xyz && out, "bias_mask_head: null pointer");
@@ -299,9 +316,11 @@ extern "C" int gf_bias_mask_head(const float *geo, const float *coords, const fl
     return GF_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  GF_CUDA(cudaMemsetAsync(rowmax, 0, sizeof(uint32_t) * (size_t)Q, st));
-  bias_init_kernel<<<1, 1, 0, st>>>(gmax);
-  GF_LAUNCHED();
+  if (!row_max) {
+    GF_CUDA(cudaMemsetAsync(rowmax, 0, sizeof(uint32_t) * (size_t)Q, st));
+    bias_init_kernel<<<1, 1, 0, st>>>(gmax);
+    GF_LAUNCHED();
+  }
   // 16-byte path: N a multiple of 4 and all bases 16-byte aligned (torch allocations are)
   const bool vec = (N % 4 == 0) && ((((uintptr_t)geo | (uintptr_t)coords | (uintptr_t)out) & 15) == 0);
   const int work = vec ? N / 4 : N;
@@ -309,7 +328,9 @@ extern "C" int gf_bias_mask_head(const float *geo, const float *coords, const fl
   if (chunks < 1) chunks = 1;
   if (chunks > (work + 1023) / 1024) chunks = (work + 1023) / 1024;
   if (chunks < 1) chunks = 1;
-  if (vec)
+  if (row_max)
+    bias_rowmax_import_kernel<<<1, 1024, 0, st>>>(row_max, Q, rowmax, gmax);
+  else if (vec)
     bias_mask_rowmax_kernel<true><<<Q * chunks, 256, 0, st>>>(geo, N, chunks, rowmax, gmax);
   else
     bias_mask_rowmax_kernel<false><<<Q * chunks, 256, 0, st>>>(geo, N, chunks, rowmax, gmax);

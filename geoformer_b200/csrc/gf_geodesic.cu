@@ -55,6 +55,7 @@ struct GeoArgs {
   int *overflow;              // per CTA: N + 2 frontier entries beyond GEO_QCAP (two stacks, one per end)
   unsigned *seed_counter;     // work distribution
   unsigned long long *stats;  // [0] reached pairs, [1] deepest level (atomicMax)
+  float *row_max;             // optional (Q): max of every finished row, a by-product for the mask-head epilogue
   int bitmap_words;           // shared-memory visited bitmap size (0 = test the output row instead)
   // seed-sharded scenes: finished rows are also stored into the other ranks' matrices (NVLink peer memory)
   int n_peers;
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
   uint32_t *vis = reinterpret_cast<uint32_t *>(q1 + GEO_QCAP);
   uint32_t *clm = vis + a.bitmap_words;
   __shared__ int s_next_n[2], s_seed_q;  // next-frontier counter, by level parity
+  __shared__ uint32_t s_rmax[GEO_THREADS / 32];
 
   const int N = a.N;
   const unsigned sb = (unsigned)a.slot_bits, KP = 1u << sb;
@@ -208,10 +210,13 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
     int level = 0;
     // Distance of a point won at level `won`: the key left in its row entry is the reference's winner.
     // level 1: the distance is the edge itself (:127); later: edge + parent's distance (:144)
+    float rmax = 0.f;  // largest distance this thread wrote into the row (all are >= 0)
     auto resolve_finish = [&](int t, uint32_t key, int won) {
       const unsigned p = (key & 0x7fffffffu) >> sb, j = key & (KP - 1);
       const float w = __ldg(a.len + ((size_t)p << sb) + j);
-      row[t] = won == 1 ? w : __fadd_rn(w, __uint_as_float(ld_cg_u32(rowu + p)));  // :139
+      const float d = won == 1 ? w : __fadd_rn(w, __uint_as_float(ld_cg_u32(rowu + p)));  // :139
+      row[t] = d;
+      rmax = fmaxf(rmax, d);
     };
     auto frontier_at = [&](const int *q, int i, int won) { return i < GEO_QCAP ? q[i] : ovf[ovf_index(i, won & 1, N)]; };
     while (F > 0 && level < a.max_step) {
@@ -274,7 +279,9 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
       if (BITMAP && level > 1) {  // finish the resolve of the points won at level-1
         if (rt >= 0) {
           if (!rissued) resolve_issue();
-          row[rt] = level == 2 ? rw : __fadd_rn(rw, rpd);  // :127 / :139,:144
+          const float d = level == 2 ? rw : __fadd_rn(rw, rpd);  // :127 / :139,:144
+          row[rt] = d;
+          rmax = fmaxf(rmax, d);
         }
         for (int i = tid + GEO_THREADS; i < F; i += GEO_THREADS) {
           const int t = frontier_at(fq, i, level - 1);
@@ -344,6 +351,18 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
       }
     }
     if (level == 0 && seed_ok && tid == 0) row[s] = 0.f;  // max_step <= 0: only the seed entry (:118)
+    if (a.row_max) {
+      // max over the row = max over what was written (the seed's 0 included), or -1 for a row that stayed empty;
+      // distances are non-negative, so their bit patterns order like unsigned integers
+      const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(rmax));
+      if ((tid & 31u) == 0) s_rmax[tid >> 5] = wm;
+      __syncthreads();
+      if (tid < 32) {
+        const uint32_t v = tid < GEO_THREADS / 32 ? s_rmax[tid] : 0u;
+        const uint32_t m = __reduce_max_sync(0xffffffffu, v);
+        if (tid == 0) a.row_max[q] = seed_ok ? __uint_as_float(m) : -1.f;
+      }
+    }
     if (a.n_peers > 0) {
       // The row is final: push it into every peer's matrix now, while other CTAs are still propagating --
       // the exchange of a seed-sharded scene rides under the compute instead of following it as a
@@ -461,7 +480,7 @@ size_t geodesic_workspace_bytes(int N, int k, int Q) {
 
 int geodesic_run(const float *D, const void *I, int is64, int N, int k, const int *seeds, int Q, float radius,
                  int max_step, float *geo, int64_t *stats_out, void *workspace, size_t workspace_bytes,
-                 cudaStream_t st, float *const *peer_rows, int n_peers) {
+                 cudaStream_t st, float *const *peer_rows, int n_peers, float *row_max) {
   if (n_peers < 0 || n_peers > GEO_MAX_PEERS || (n_peers > 0 && !peer_rows)) {
     set_error("geodesic: %d peers given, at most %d supported", n_peers, GEO_MAX_PEERS);
     return GF_ERR_INVALID;
@@ -503,6 +522,7 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
   ga.tgt = tgt, ga.len = len, ga.N = N, ga.Q = Q, ga.max_step = max_step, ga.slot_bits = slot_bits;
   ga.seeds = seeds, ga.geo = geo, ga.overflow = overflow, ga.seed_counter = counter, ga.stats = stats;
   ga.bitmap_words = p.bitmap_words;
+  ga.row_max = row_max;
   ga.n_peers = n_peers;
   for (int r = 0; r < GEO_MAX_PEERS; ++r) ga.peer_geo[r] = r < n_peers ? peer_rows[r] : nullptr;
   for (int r = 0; r < n_peers; ++r)
@@ -567,14 +587,14 @@ extern "C" size_t gf_geodesic_workspace_bytes(int N, int k, int Q) {
 }
 
 extern "C" int gf_geodesic(const float *knn_dist, const void *knn_idx, int idx_is_i64, int N, int k, const int *seeds,
-                           int Q, float radius, int max_step, float *geo, int64_t *stats, void *workspace,
-                           size_t workspace_bytes, void *stream) {
+                           int Q, float radius, int max_step, float *geo, int64_t *stats, float *row_max,
+                           void *workspace, size_t workspace_bytes, void *stream) {
   GF_CHECK_ARG(N >= 0 && Q >= 0, "geodesic: negative size");
   GF_CHECK_ARG(k >= 1 && k <= 256, "geodesic: k=%d outside [1,256]", k);
   if (N == 0 || Q == 0) return GF_OK;
   GF_CHECK_ARG(knn_dist && knn_idx && seeds && geo, "geodesic: null pointer");
   return geodesic_run(knn_dist, knn_idx, idx_is_i64, N, k, seeds, Q, radius, max_step, geo, stats, workspace,
-                      workspace_bytes, (cudaStream_t)stream, nullptr, 0);
+                      workspace_bytes, (cudaStream_t)stream, nullptr, 0, row_max);
 }
 
 extern "C" int gf_geodesic_scatter(const float *knn_dist, const void *knn_idx, int idx_is_i64, int N, int k,

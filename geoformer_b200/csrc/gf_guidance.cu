@@ -56,7 +56,7 @@ extern "C" size_t gf_guidance_workspace_bytes(int N, int Q, int k) {
 static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, int max_step, int *seeds,
                          int seeds_given, float *geo, float *knn_dist, int32_t *knn_idx32, int64_t *stats,
                          void *workspace, size_t workspace_bytes, void *stream, float *const *peer_geo = nullptr,
-                         int n_peers = 0) {
+                         int n_peers = 0, float *row_max = nullptr) {
   GF_CHECK_ARG(N >= 1 && Q >= 1, "guidance: need N >= 1 and Q >= 1 (N=%d Q=%d)", N, Q);
   GF_CHECK_ARG(k >= 1 && k <= KNN_MAX_K, "guidance: k=%d outside [1,%d]", k, KNN_MAX_K);
   GF_CHECK_ARG(xyz && seeds && geo, "guidance: null pointer");
@@ -101,21 +101,21 @@ static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, in
   if (!seeds_given) GF_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   stage_mark(ST_KNN_DONE, st);
   return geodesic_run(dist, idx, /*is64=*/0, N, k, seeds, Q, radius, max_step, geo, stats, ws_geo, p.geo, st, peer_geo,
-                      n_peers);
+                      n_peers, row_max);
 }
 
 extern "C" int gf_guidance(const float *xyz, int N, int Q, int k, float radius, int max_step, int *seeds, float *geo,
-                           float *knn_dist, int32_t *knn_idx32, int64_t *stats, void *workspace,
+                           float *knn_dist, int32_t *knn_idx32, int64_t *stats, float *row_max, void *workspace,
                            size_t workspace_bytes, void *stream) {
   return guidance_impl(xyz, N, Q, k, radius, max_step, seeds, 0, geo, knn_dist, knn_idx32, stats, workspace,
-                       workspace_bytes, stream);
+                       workspace_bytes, stream, nullptr, 0, row_max);
 }
 
 extern "C" int gf_guidance_seeded(const float *xyz, int N, const int *seeds, int Q, int k, float radius, int max_step,
-                                  float *geo, float *knn_dist, int32_t *knn_idx32, int64_t *stats, void *workspace,
-                                  size_t workspace_bytes, void *stream) {
+                                  float *geo, float *knn_dist, int32_t *knn_idx32, int64_t *stats, float *row_max,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
   return guidance_impl(xyz, N, Q, k, radius, max_step, const_cast<int *>(seeds), 1, geo, knn_dist, knn_idx32, stats,
-                       workspace, workspace_bytes, stream);
+                       workspace, workspace_bytes, stream, nullptr, 0, row_max);
 }
 
 extern "C" int gf_guidance_seeded_scatter(const float *xyz, int N, const int *seeds, int Q, int k, float radius,
@@ -151,7 +151,7 @@ extern "C" int gf_guidance_host(const float *xyz_host, int N, int Q, int k, floa
   w += align256(sizeof(float) * (size_t)Q * N);
   size_t inner = plan_guidance(N, Q, k).total;
   GF_CUDA(cudaMemcpyAsync(d_xyz, xyz_host, sizeof(float) * (size_t)N * 3, cudaMemcpyHostToDevice, st));
-  int rc = gf_guidance(d_xyz, N, Q, k, radius, max_step, d_seeds, d_geo, nullptr, nullptr, nullptr, w, inner, st);
+  int rc = gf_guidance(d_xyz, N, Q, k, radius, max_step, d_seeds, d_geo, nullptr, nullptr, nullptr, nullptr, w, inner, st);
   if (rc) return rc;
   GF_CUDA(cudaMemcpyAsync(seeds_host, d_seeds, sizeof(int) * (size_t)Q, cudaMemcpyDeviceToHost, st));
   GF_CUDA(cudaMemcpyAsync(geo_host, d_geo, sizeof(float) * (size_t)Q * N, cudaMemcpyDeviceToHost, st));

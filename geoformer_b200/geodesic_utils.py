@@ -98,7 +98,7 @@ def unique_with_inds(x, dim=-1):
     return unique, first
 
 
-def geodesic_from_graph(D, I, seeds, radius, max_step, return_stats=False):
+def geodesic_from_graph(D, I, seeds, radius, max_step, return_stats=False, row_max=None):
     """Propagation only (geodesic_utils.py:109-163) on a given kNN graph: D (N,k) sqrt'ed f32,
     I (N,k) int64/int32, seeds (Q,) int32/int64 -> (Q,N) f32, -1 = unreachable."""
     C.check_cuda_f32(D, "D")
@@ -113,12 +113,13 @@ def geodesic_from_graph(D, I, seeds, radius, max_step, return_stats=False):
         nbytes = L.gf_geodesic_workspace_bytes(N, k, Q)
         ws = C.workspace.get(D.device, "geodesic", nbytes) if nbytes else None
         C.check(L.gf_geodesic(C.ptr(D), C.ptr(I), 1 if I.dtype == torch.int64 else 0, N, k, C.ptr(seeds), Q,
-                              ctypes.c_float(float(radius)), int(max_step), C.ptr(geo), C.ptr(stats),
+                              ctypes.c_float(float(radius)), int(max_step), C.ptr(geo), C.ptr(stats), C.ptr(row_max),
                               C.ptr(ws), nbytes, C.stream_of(D.device)), "geodesic")
     return (geo, stats) if return_stats else geo
 
 
-def geodesic_from_points(locs, seeds, neighbor, radius, max_step, return_graph=False, return_stats=False):
+def geodesic_from_points(locs, seeds, neighbor, radius, max_step, return_graph=False, return_stats=False,
+                         row_max=None):
     """kNN graph + propagation of one scene in one library call (the body of the reference loop,
     geodesic_utils.py:98-163)."""
     C.check_cuda_f32(locs, "locs")
@@ -134,8 +135,8 @@ def geodesic_from_points(locs, seeds, neighbor, radius, max_step, return_graph=F
         nbytes = L.gf_guidance_workspace_bytes(N, Q, int(neighbor))
         ws = C.workspace.get(locs.device, "guidance", nbytes)
         C.check(L.gf_guidance_seeded(C.ptr(locs), N, C.ptr(seeds), Q, int(neighbor), ctypes.c_float(float(radius)),
-                                     int(max_step), C.ptr(geo), C.ptr(D), C.ptr(I), C.ptr(stats), C.ptr(ws), nbytes,
-                                     C.stream_of(locs.device)), "guidance_seeded")
+                                     int(max_step), C.ptr(geo), C.ptr(D), C.ptr(I), C.ptr(stats), C.ptr(row_max),
+                                     C.ptr(ws), nbytes, C.stream_of(locs.device)), "guidance_seeded")
     out = [geo]
     if return_graph:
         out += [D, I]

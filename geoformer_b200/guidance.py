@@ -12,8 +12,10 @@ import torch
 from . import _capi as C
 
 
-def geodesic_guidance(xyz, n_queries, neighbor, radius, max_step, return_graph=False, return_stats=False):
-    """xyz (N,3) f32 CUDA -> (seeds (Q,) i32, geo (Q,N) f32 [, D (N,k) f32, I (N,k) i32][, stats (2,) i64])."""
+def geodesic_guidance(xyz, n_queries, neighbor, radius, max_step, return_graph=False, return_stats=False,
+                      row_max=None):
+    """xyz (N,3) f32 CUDA -> (seeds (Q,) i32, geo (Q,N) f32 [, D (N,k) f32, I (N,k) i32][, stats (2,) i64]).
+    row_max: optional (Q,) f32 CUDA tensor that receives the maximum of every row of geo (for the epilogues)."""
     C.check_cuda_f32(xyz, "xyz")
     C.require(xyz.dim() == 2 and xyz.size(1) == 3, "xyz must be (N, 3)")
     N, Q, k = xyz.size(0), int(n_queries), int(neighbor)
@@ -28,8 +30,8 @@ def geodesic_guidance(xyz, n_queries, neighbor, radius, max_step, return_graph=F
         nbytes = L.gf_guidance_workspace_bytes(N, Q, k)
         ws = C.workspace.get(dev, "guidance", nbytes)
         C.check(L.gf_guidance(C.ptr(xyz), N, Q, k, ctypes.c_float(float(radius)), int(max_step), C.ptr(seeds),
-                              C.ptr(geo), C.ptr(D), C.ptr(I), C.ptr(stats), C.ptr(ws), nbytes, C.stream_of(dev)),
-                "guidance")
+                              C.ptr(geo), C.ptr(D), C.ptr(I), C.ptr(stats), C.ptr(row_max), C.ptr(ws), nbytes,
+                              C.stream_of(dev)), "guidance")
     out = [seeds, geo]
     if return_graph:
         out += [D, I]
@@ -49,6 +51,7 @@ class GuidanceRunner:
         self.seeds = torch.empty((self.Q,), dtype=torch.int32, device=self.device)
         self.geo = torch.empty((self.Q, self.N), dtype=torch.float32, device=self.device)
         self.stats = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.row_max = torch.empty((self.Q,), dtype=torch.float32, device=self.device)
         self._L = C.lib()
         self._nbytes = self._L.gf_guidance_workspace_bytes(self.N, self.Q, self.k)
         self._ws = torch.empty(self._nbytes, dtype=torch.uint8, device=self.device)
@@ -57,7 +60,8 @@ class GuidanceRunner:
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         C.check(self._L.gf_guidance(C.ptr(xyz), self.N, self.Q, self.k, ctypes.c_float(self.radius), self.max_step,
                                     C.ptr(self.seeds), C.ptr(self.geo), None, None, C.ptr(self.stats),
-                                    C.ptr(self._ws), self._nbytes, ctypes.c_void_p(st.cuda_stream)), "guidance")
+                                    C.ptr(self.row_max), C.ptr(self._ws), self._nbytes,
+                                    ctypes.c_void_p(st.cuda_stream)), "guidance")
         return self.seeds, self.geo
 
 

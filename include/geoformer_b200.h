@@ -104,11 +104,13 @@ int gf_knn(const float *xyz, int N, const float *queries, int nq, int k, int sqr
  * dropped like the reference (:110-111).  seeds (Q) i32.  geo (Q,N) f32, -1 = unreachable.
  * Level-synchronous first-visit BFS; within a level the parent with the smallest index, then the
  * smallest neighbour slot, wins.  Needs N << ceil(log2(k-1)) < 2^30.
- * stats (2) i64 device, optional: [0] = reached (q,p) pairs, [1] = deepest level reached.        */
+ * stats (2) i64 device, optional: [0] = reached (q,p) pairs, [1] = deepest level reached.
+ * row_max (Q) f32 device, optional: the maximum of every row of geo (a by-product of the propagation;
+ * -1 for a row that stayed empty) -- what both epilogues start from (geoformer_fs.py:274-275).      */
 size_t gf_geodesic_workspace_bytes(int N, int k, int Q);
 int gf_geodesic(const float *knn_dist, const void *knn_idx, int idx_is_i64, int N, int k, const int *seeds, int Q,
-                float radius, int max_step, float *geo, int64_t *stats, void *workspace, size_t workspace_bytes,
-                void *stream);
+                float radius, int max_step, float *geo, int64_t *stats, float *row_max, void *workspace,
+                size_t workspace_bytes, void *stream);
 
 /* ---- distance -> bias epilogues ------------------------------------------------------------- */
 
@@ -130,9 +132,10 @@ int gf_bias_decoder_fourier(const float *const *geo_ptrs, const int *geo_ld, con
                             int d_out, int gauss_ld, const float *pc_min, const float *pc_max, float *out,
                             void *workspace, size_t workspace_bytes, void *stream);
 /* mask-head relative coordinates (geoformer_fs.py:263-292):
- * geo (Q,N), coords (N,3), seed_xyz (Q,3) -> out (Q,3,N).                                       */
-int gf_bias_mask_head(const float *geo, const float *coords, const float *seed_xyz, int Q, int N, float *out,
-                      void *workspace, size_t workspace_bytes, void *stream);
+ * geo (Q,N), coords (N,3), seed_xyz (Q,3) -> out (Q,3,N).  row_max (Q) optional: the row maxima as
+ * returned by gf_geodesic / gf_guidance; when given, geo is read once instead of twice.          */
+int gf_bias_mask_head(const float *geo, const float *coords, const float *seed_xyz, int Q, int N,
+                      const float *row_max, float *out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- fused hot path: FPS -> kNN -> geodesic -------------------------------------------------- */
 
@@ -140,14 +143,14 @@ int gf_bias_mask_head(const float *geo, const float *coords, const float *seed_x
  * may be NULL (kept in the workspace).                                                           */
 size_t gf_guidance_workspace_bytes(int N, int Q, int k);
 int gf_guidance(const float *xyz, int N, int Q, int k, float radius, int max_step, int *seeds, float *geo,
-                float *knn_dist, int32_t *knn_idx32, int64_t *stats, void *workspace, size_t workspace_bytes,
-                void *stream);
+                float *knn_dist, int32_t *knn_idx32, int64_t *stats, float *row_max, void *workspace,
+                size_t workspace_bytes, void *stream);
 
 /* Same, with the seeds given (the body of cal_geodesic_vectorize for one scene, geodesic_utils.py:98-163:
  * kNN of the scene against itself, then the propagation from pre_enc_inds[b][:n_queries]).       */
 int gf_guidance_seeded(const float *xyz, int N, const int *seeds, int Q, int k, float radius, int max_step,
-                       float *geo, float *knn_dist, int32_t *knn_idx32, int64_t *stats, void *workspace,
-                       size_t workspace_bytes, void *stream);
+                       float *geo, float *knn_dist, int32_t *knn_idx32, int64_t *stats, float *row_max,
+                       void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- one scene over several GPUs, split by seed blocks --------------------
  * New with this library (the reference is single-GPU, train.py:156-185).  Every rank holds the whole

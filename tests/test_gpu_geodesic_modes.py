@@ -34,8 +34,10 @@ for N, room, Q, k, r, ms in cases:
     seeds = oracle.furthest_point_sampling(x[None].numpy(), Q)[0]
     D, I = knn_graph(x.to(dev), k)
     want = oracle.geodesic(D.cpu().numpy(), I.cpu().numpy(), seeds, r, ms)
-    got = geodesic_from_graph(D, I, torch.from_numpy(seeds).to(dev), r, ms).cpu().numpy()
+    rm = torch.zeros(Q, device=dev)
+    got = geodesic_from_graph(D, I, torch.from_numpy(seeds).to(dev), r, ms, row_max=rm).cpu().numpy()
     assert np.array_equal(got, want), (N, Q, k, r, ms, int((got != want).sum()))
+    assert np.array_equal(rm.cpu().numpy(), want.max(axis=1)), "row_max by-product"
     print("ok", N, Q, k, r, ms, "reached", int((want >= 0).sum()))
 """
 

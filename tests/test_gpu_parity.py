@@ -408,6 +408,36 @@ def test_bias_epilogues(oracle_lib, dev):
         assert torch.equal(m, rm)
 
 
+def test_row_max_by_product(oracle_lib, dev):
+    """The propagation can hand out the maximum of every row (what both epilogues start from); it must be
+    exactly geo.max(dim=1), also for rows that stay empty, and the mask-head epilogue fed with it must
+    produce the same bits as when it reduces the maps itself."""
+    from geoformer_b200.bias import mask_head_relative_coords
+    from geoformer_b200.geodesic_utils import geodesic_from_graph, geodesic_from_points, knn_graph
+    from geoformer_b200.guidance import geodesic_guidance
+
+    x = scene(30000, 21).to(dev)
+    for ms in (0, 1, 2, 7, 40):
+        rm = torch.full((48,), 123.0, device=dev)
+        seeds, geo = geodesic_guidance(x, 48, 16, 0.5, ms, row_max=rm)
+        assert torch.equal(rm, geo.max(dim=1).values), ms
+        out_a = mask_head_relative_coords(geo, x, x[seeds.long()].contiguous(), row_max=rm)
+        out_b = mask_head_relative_coords(geo, x, x[seeds.long()].contiguous())
+        assert torch.equal(out_a, out_b), ms
+    # seeded entry points, out-of-range seeds (rows stay -1), duplicate seeds, unaligned N
+    x2 = scene(10001, 22).to(dev)
+    D, I = knn_graph(x2, 8)
+    seeds = torch.tensor([5, -1, 10001, 5, 9999, 0], dtype=torch.int32, device=dev)
+    rm = torch.zeros(6, device=dev)
+    geo = geodesic_from_graph(D, I, seeds, 0.3, 12, row_max=rm)
+    assert torch.equal(rm, geo.max(dim=1).values) and rm[1] == -1 and rm[2] == -1
+    rm2 = torch.zeros(6, device=dev)
+    geo2 = geodesic_from_points(x2, seeds, 8, 0.3, 12, row_max=rm2)
+    assert torch.equal(geo2, geo) and torch.equal(rm2, rm)
+    sx = x2[seeds.clamp(0, 10000).long()].contiguous()
+    assert torch.equal(mask_head_relative_coords(geo, x2, sx, row_max=rm), mask_head_relative_coords(geo, x2, sx))
+
+
 def test_decoder_fourier_embedding(dev):
     """geoformer_fs.py:680-712 fused (gather -> fill -> normalise -> 3x32 projection -> sin|cos) against the
     fixture produced by the reference's own PositionEmbeddingCoordsSine, and against the torch restatement
