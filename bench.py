@@ -432,6 +432,40 @@ def run_ours(args):
                         "shares the SMs with the next scenes' FPS / kNN kernels; *_alone = serial pass" % nstreams,
                 "compulsory_bytes": 12.0 * N + 8.0 * N * k + 4.0 * Q * N}
 
+    # traffic was captured for c2 at 32 levels only
+    if not (args.workload == "c2" and cfg["max_step"] == 32):
+        roofline["traffic"] = None
+
+    # ---- the reference's evaluation setting (max_step = 256, geoformer_fs.py:502; SURVEY 8: "additionally
+    #      report max_step=256"): same scene, serial pass, propagation kernel only ---------------------------
+    eval_setting = None
+    if args.workload == "c2" and cfg["max_step"] == 32 and world == 1:
+        try:
+            r256 = GuidanceRunner(N, Q, k, cfg["radius"], 256, device=dev)
+            Ke = 6
+            ev_e = [[L.gf_event_create() for _ in range(5)] for _ in range(Ke)]
+            arr_e = [(ctypes.c_void_p * 5)(*e) for e in ev_e]
+            for i in range(Ke):
+                L.gf_set_stage_events(arr_e[i], 5)
+                r256.run(xs[i % S], stream)
+            torch.cuda.synchronize(dev)
+            v = [L.gf_event_elapsed_ms(e[3], e[4]) for e in ev_e[2:]]
+            w = [L.gf_event_elapsed_ms(e[0], e[4]) for e in ev_e[2:]]
+            for e in ev_e:
+                for h in e:
+                    L.gf_event_destroy(h)
+            R256 = int(r256.stats[0].item())
+            b256 = 4.0 * Q * N + (R256 + Q) * Kn * 12.0 + 4.0 * R256
+            t256 = statistics.mean(v)
+            eval_setting = {"max_step": 256, "levels_run": int(r256.stats[1].item()), "reached_pairs_R": R256,
+                            "propagation_ms_alone": t256, "whole_call_ms_alone": statistics.mean(w),
+                            "maps_per_s_alone": Q / (statistics.mean(w) * 1e-3),
+                            "algorithmic_bytes_per_launch": b256, "achieved_alone": b256 / (t256 * 1e-3) / 1e9,
+                            "frac_alone": b256 / (t256 * 1e-3) / 1e9 / peak}
+            del r256
+        except Exception as ex:
+            eval_setting = {"error": repr(ex)}
+
     # ---- the two distance -> bias epilogues, timed on their own ---------------------
     epilogues = None
     try:
@@ -553,7 +587,8 @@ def run_ours(args):
                 "l2": "%d rotating scenes per rank, %.0f MB footprint each (> 126 MB L2 in total)" % (S, per_scene / 1e6),
                 "streams": nstreams}),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "stage_ms": stage_ms, "stage_ms_serial": stage_ms_serial, "epilogues": epilogues, "scenes_per_s": value / Q,
+            "stage_ms": stage_ms, "stage_ms_serial": stage_ms_serial, "epilogues": epilogues,
+            "eval_setting_max_step_256": eval_setting, "scenes_per_s": value / Q,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -13,25 +13,27 @@
 // synchronisation is a __syncthreads() -- no grid barrier, no host round trip (the reference
 // synchronises the host >= 3 times per level).  Per seed, in shared memory: the visited bitmap, a
 // "claimed at this level" bitmap and the compacted frontier queue (point ids).  The seed's own output
-// row geo[q][:] doubles as the claim array:
-//   pass A  a group of KP lanes expands one frontier point p (lane = neighbour slot j, one aligned
-//           128-byte load of packed {target, length} edges at k = 16).  An edge to an unvisited t claims
-//           it with a fire-and-forget  RED.MIN(bits(geo[q][t]), 0x80000000 | p << SB | j):  smaller than
-//           "unvisited" (-1.0f = 0xBF800000), larger than any finished distance (a non-negative float),
-//           and ordered exactly like the reference's tie rule (parent index, then slot).  A test-and-set
-//           on the claimed bitmap (shared-memory atomic, ~100 cycles) tells the first claimant of t, which
-//           appends t to the next frontier -- no atomic return value is ever waited for.
-//   pass B  (after the CTA barrier) for every new point the key left in its row entry IS the reference's
-//           winner: decode (p, j), read the edge length and p's finished distance, write
-//           geo[q][t] = D[p][j] + geo[q][p] (one fp32 add, as the reference), move the claimed bit to the
-//           visited bitmap.
-// The inner loop has no bounds or validity branches: frontier queues are padded with the sentinel point N,
-// whose edge row holds only edges to N, and bit N of the visited bitmap is always set, so padding and
-// filtered edges (radius / missing neighbour, :123 / :151, applied once when the graph is packed) look
-// like edges to an already visited point.  ~20 instructions per edge instead of ~120 for the earlier
-// hash-table formulation (both measured).
-// Levels whose frontier does not fit the on-chip queue read its tail from a global overflow area;
-// scenes too large for the two bitmaps (N > ~800k) test / claim through the row with returning atomics.
+// row geo[q][:] doubles as the claim array.  One level:
+//   claims   KP/4 lanes expand one frontier point p, each lane fetching four edge targets with one 16-byte
+//            load.  An edge to an unvisited t claims it with a fire-and-forget
+//            RED.MIN(bits(geo[q][t]), 0x80000000 | p << SB | j): smaller than "unvisited" (-1.0f =
+//            0xBF800000), larger than any finished distance (a non-negative float), and ordered exactly
+//            like the reference's tie rule (parent index, then slot); plus a fire-and-forget ATOMS.OR on
+//            the claimed bitmap.  No atomic return value is ever waited for.
+//   resolve  of the PREVIOUS level's winners, started before the claims and finished under them: the key
+//            left in a point's row entry IS the reference's winner: decode (p, j), read the edge length and
+//            p's finished distance, write geo[q][t] = D[p][j] + geo[q][p] (one fp32 add, as the reference).
+//   commit   (after the CTA barrier) every thread owns whole 16-byte pieces of the bitmaps: claimed ->
+//            visited, claimed cleared, set bits enumerated into the frontier queue of the next level.
+// The claim loop has no bounds or validity branches: lanes past the end of the queue expand the sentinel
+// point N, whose edge row holds only edges to N, and bit N of the visited bitmap is always set, so padding
+// and filtered edges (radius / missing neighbour, :123 / :151, applied once when the graph is packed) look
+// like edges to an already visited point.
+// Levels whose frontier does not fit the on-chip queue read its tail from a global overflow area; scenes too
+// large for the two bitmaps (N > ~860k) test / claim through the row with returning atomics (MODE 0; MODE 1
+// keeps only the visited bitmap on chip).  Optional by-products: the maximum of every row (for the
+// epilogues) and, for seed-sharded scenes, the finished row pushed into the peers' matrices over NVLink.
+// History of the formulations that were measured and replaced: DESIGN.md section 4.3.
 #include <stdlib.h>
 
 #include "gf_geodesic.cuh"
