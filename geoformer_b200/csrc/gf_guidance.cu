@@ -3,6 +3,8 @@
 // libraries and a Python loop).  FPS (a <= 16-SM cluster kernel, latency bound) runs on a forked
 // stream concurrently with the kNN graph construction (which fills the other SMs); the geodesic
 // waits for both.
+#include <stdlib.h>
+
 #include "gf_geodesic.cuh"
 #include "gf_knn.cuh"
 
@@ -13,18 +15,49 @@ struct ForkJoin {
   cudaEvent_t fork = nullptr, join = nullptr;
 };
 
-static int get_fork_join(ForkJoin **out) {
-  static thread_local ForkJoin fj[64];
+// One auxiliary stream per (device, caller stream) of the calling thread, so that callers that keep several
+// scenes in flight on several streams also get their FPS kernels (one 16-SM cluster each, latency bound)
+// running side by side instead of queueing on a single hidden stream.  Highest priority: FPS is the longest
+// dependency chain of a step, its cluster should be placed as soon as SMs free up.
+static int get_fork_join(cudaStream_t user, ForkJoin **out) {
+  constexpr int SLOTS = 16;
+  struct Entry {
+    int dev;
+    cudaStream_t user;
+    ForkJoin fj;
+    bool used;
+  };
+  static thread_local Entry pool[SLOTS];
+  static thread_local int next_victim = 0;
   int dev = 0;
   GF_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) dev = 0;
-  ForkJoin &f = fj[dev];
-  if (f.aux == nullptr) {
-    GF_CUDA(cudaStreamCreateWithFlags(&f.aux, cudaStreamNonBlocking));
-    GF_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
-    GF_CUDA(cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming));
+  Entry *e = nullptr;
+  for (int i = 0; i < SLOTS; ++i)
+    if (pool[i].used && pool[i].dev == dev && pool[i].user == user) e = &pool[i];
+  if (!e) {
+    for (int i = 0; i < SLOTS && !e; ++i)
+      if (!pool[i].used) e = &pool[i];
+    if (!e) {  // more caller streams than slots: share (correct, only less concurrent)
+      e = &pool[next_victim];
+      next_victim = (next_victim + 1) % SLOTS;
+      if (e->dev != dev) e = nullptr;
+    }
+    if (e && !e->used) {
+      int lo = 0, hi = 0;
+      GF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = greatest priority
+      GF_CUDA(cudaStreamCreateWithPriority(&e->fj.aux, cudaStreamNonBlocking, hi));
+      GF_CUDA(cudaEventCreateWithFlags(&e->fj.fork, cudaEventDisableTiming));
+      GF_CUDA(cudaEventCreateWithFlags(&e->fj.join, cudaEventDisableTiming));
+      e->used = true;
+      e->dev = dev;
+    }
+    if (e) e->user = user;
   }
-  *out = &f;
+  if (!e) {
+    set_error("guidance: no auxiliary stream available on device %d", dev);
+    return GF_ERR_CUDA;
+  }
+  *out = &e->fj;
   return GF_OK;
 }
 
@@ -81,7 +114,7 @@ static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, in
   int rc = GF_OK;
   stage_mark(ST_BEGIN, st);
   if (!seeds_given) {
-    rc = get_fork_join(&fj);
+    rc = get_fork_join(st, &fj);
     if (rc) return rc;
     // fork: FPS on the auxiliary stream
     GF_CUDA(cudaEventRecord(fj->fork, st));
