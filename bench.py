@@ -361,9 +361,11 @@ def run_ours(args):
     for st_ in side:
         if st_ is not stream:
             st_.wait_event(e0)
+    t_host0 = time.perf_counter()
     for i in range(K):
         L.gf_set_stage_events(ev_arr[i], 5)
         runners[i % S].run(xs[i % S], side[i % nstreams])
+    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host0) / K
     for st_ in side:
         if st_ is not stream:
             done = torch.cuda.Event()
@@ -589,6 +591,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stage_ms": stage_ms, "stage_ms_serial": stage_ms_serial, "epilogues": epilogues,
             "eval_setting_max_step_256": eval_setting, "scenes_per_s": value / Q,
+            "host_enqueue_ms_per_step": host_enqueue_ms,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
