@@ -247,12 +247,18 @@ __global__ void __launch_bounds__(T, 1)
 // polls all slots, reduces them with REDUX and hands the winner to the CTA through shared memory.  ~2.5 us per round instead of ~25 us for
 // the one-cluster streaming kernel at 1 M points.
 constexpr int FPS_GRID_T = 256;
+constexpr int FPS_MAX_GRID_CTAS = 160;  // >= the SM count of the device (148 on B200); checked at launch
 
 constexpr int FPS_SLOT_WORDS = 8;  // 64-byte slots: {v,tag} {lo,tag} {x,tag} {y,tag} {z,tag} + padding
 // strong (gpu-scope, relaxed) 64-bit accesses: single-copy atomic and coherent across both L2 partitions
 __device__ __forceinline__ void st_cg_v2(uint2 *p, uint32_t payload, uint32_t tag) {
   const unsigned long long w = ((unsigned long long)tag << 32) | payload;
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const uint2 *p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
 }
 __device__ __forceinline__ uint32_t poll_word(const uint2 *p, uint32_t tag) {
   unsigned long long w;
@@ -364,21 +370,47 @@ __global__ void __launch_bounds__(FPS_GRID_T, 1)
         st_cg_v2(dst + 3, __float_as_uint(by), tag);
         st_cg_v2(dst + 4, __float_as_uint(bz), tag);
       }
-      if (warp == 0) {  // poll every CTA's slot of this round, keep the best key seen by this lane
+      if (warp == 0) {
+        // Poll every CTA's slot of this round.  The key words of all of this lane's slots are requested
+        // together (up to 5 slots x 2 words in flight) and only the slots whose tags are not there yet are
+        // asked again; the coordinates are fetched from the winning slot alone.  Word-by-word spinning cost
+        // one L2 round trip per word, and polling all five words of every slot made the 148 x 32 pollers
+        // congest the few L2 lines that hold the slots.
+        constexpr int MAXS = (FPS_MAX_GRID_CTAS + 31) / 32;
         uint32_t gv = 0, gl = 0, src = 0;
-        for (unsigned r = lane; r < nctas; r += 32) {
-          const uint2 *sp = slots + ((size_t)buf * nctas + r) * FPS_SLOT_WORDS;
-          const uint32_t sv = poll_word(sp + 0, tag), sl = poll_word(sp + 1, tag);
-          if (sv > gv || (sv == gv && sl > gl)) gv = sv, gl = sl, src = r;
+        unsigned pend = 0;
+#pragma unroll
+        for (int sI = 0; sI < MAXS; ++sI)
+          if (lane + 32u * sI < nctas) pend |= 1u << sI;
+        while (pend) {
+          unsigned long long w[MAXS][2];
+#pragma unroll
+          for (int sI = 0; sI < MAXS; ++sI)
+            if ((pend >> sI) & 1u) {
+              const uint2 *sp = slots + ((size_t)buf * nctas + lane + 32u * sI) * FPS_SLOT_WORDS;
+              w[sI][0] = ld_relaxed_u64(sp + 0);
+              w[sI][1] = ld_relaxed_u64(sp + 1);
+            }
+#pragma unroll
+          for (int sI = 0; sI < MAXS; ++sI)
+            if (((pend >> sI) & 1u) && (uint32_t)(w[sI][0] >> 32) == tag && (uint32_t)(w[sI][1] >> 32) == tag) {
+              pend &= ~(1u << sI);
+              const uint32_t sv = (uint32_t)w[sI][0], sl = (uint32_t)w[sI][1];
+              if (sv > gv || (sv == gv && sl > gl)) gv = sv, gl = sl, src = lane + 32u * sI;
+            }
         }
         const uint32_t mv = __reduce_max_sync(0xffffffffu, gv);
         const uint32_t ml = __reduce_max_sync(0xffffffffu, gv == mv ? gl : 0u);
         const unsigned wm = __ballot_sync(0xffffffffu, gv == mv && gl == ml);
         if (lane == (unsigned)(__ffs(wm) - 1)) {
           const uint2 *sp = slots + ((size_t)buf * nctas + src) * FPS_SLOT_WORDS;
-          s_center[buf][0] = __uint_as_float(poll_word(sp + 2, tag));
-          s_center[buf][1] = __uint_as_float(poll_word(sp + 3, tag));
-          s_center[buf][2] = __uint_as_float(poll_word(sp + 4, tag));
+          unsigned long long x, y, z;
+          do {  // the three coordinate words of the winner, requested together
+            x = ld_relaxed_u64(sp + 2), y = ld_relaxed_u64(sp + 3), z = ld_relaxed_u64(sp + 4);
+          } while ((uint32_t)(x >> 32) != tag || (uint32_t)(y >> 32) != tag || (uint32_t)(z >> 32) != tag);
+          s_center[buf][0] = __uint_as_float((uint32_t)x);
+          s_center[buf][1] = __uint_as_float((uint32_t)y);
+          s_center[buf][2] = __uint_as_float((uint32_t)z);
           s_win[buf][0] = mv;
           s_win[buf][1] = ml;
         }
@@ -436,6 +468,7 @@ template <int P>
 static int launch_fps_grid(const float *xyz, int B, int N, int m, int L, float *temp, int *idx, uint2 *slots,
                            cudaStream_t st) {
   int ctas = num_sms() & ~1;
+  if (ctas > FPS_MAX_GRID_CTAS) ctas = FPS_MAX_GRID_CTAS;
   GF_CUDA(cudaMemsetAsync(slots, 0, sizeof(uint2) * 2 * FPS_SLOT_WORDS * (size_t)ctas, st));  // tag 0 = never written
   void *args[] = {(void *)&xyz, &B, &N, &m, &L, &temp, &idx, &slots};
   GF_CUDA(cudaLaunchCooperativeKernel((const void *)fps_grid_kernel<P>, dim3(ctas), dim3(FPS_GRID_T), args, 0, st));
