@@ -388,8 +388,11 @@ __global__ void __launch_bounds__(FPS_GRID_T, 1)
           for (int sI = 0; sI < MAXS; ++sI)
             if ((pend >> sI) & 1u) {
               const uint2 *sp = slots + ((size_t)buf * nctas + lane + 32u * sI) * FPS_SLOT_WORDS;
-              w[sI][0] = ld_relaxed_u64(sp + 0);
-              w[sI][1] = ld_relaxed_u64(sp + 1);
+              // one 16-byte request for both key words; each carries its own tag, so a torn pair is detected
+              asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
+                           : "=l"(w[sI][0]), "=l"(w[sI][1])
+                           : "l"(sp)
+                           : "memory");
             }
 #pragma unroll
           for (int sI = 0; sI < MAXS; ++sI)
