@@ -141,6 +141,22 @@ __device__ __forceinline__ void geo_claim(uint32_t key, int t, int N, int level,
 template <int MODE>
 __device__ __forceinline__ void geo_claim4(uint32_t key, const int4 t, int N, int level, uint32_t *vis, uint32_t *clm,
                                            uint32_t *rowu, int *nq, int *ovf, int *s_next_n) {
+  if (MODE == 0) {
+    // Without on-chip state both the visited test and the claim are L2 round trips.  The four tests are
+    // issued together, then the (returning) claims of the targets that passed, then the queue appends:
+    // two round trips per lane and batch instead of up to eight in sequence.
+    const int tt[4] = {t.x, t.y, t.z, t.w};
+    uint32_t st[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) st[e] = tt[e] < N ? ld_cg_u32(rowu + tt[e]) : 0u;  // 0 = "visited": padding / filtered
+    uint32_t old[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) old[e] = st[e] >= GEO_KEYBIT ? atomicMin(rowu + tt[e], key + e) : 0u;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (old[e] == GEO_UNVISITED) frontier_put(nq, ovf, atomicAdd(s_next_n, 1), level & 1, N, tt[e]);
+    return;
+  }
   geo_claim<MODE>(key + 0, t.x, N, level, vis, clm, rowu, nq, ovf, s_next_n);
   geo_claim<MODE>(key + 1, t.y, N, level, vis, clm, rowu, nq, ovf, s_next_n);
   geo_claim<MODE>(key + 2, t.z, N, level, vis, clm, rowu, nq, ovf, s_next_n);
