@@ -408,6 +408,23 @@ def test_bias_epilogues(oracle_lib, dev):
         assert torch.equal(m, rm)
 
 
+def test_guidance_runner_cuda_graph(dev):
+    """The fused path (forked FPS stream included) captured into a CUDA graph replays to the same bits, also
+    when run() is handed another scene than the captured tensor."""
+    from geoformer_b200.guidance import GuidanceRunner, geodesic_guidance
+
+    xa, xb = scene(40000, 31).to(dev), scene(40000, 32).to(dev)
+    r = GuidanceRunner(40000, 64, 16, 0.5, 20, device=dev, graph=True)
+    side = torch.cuda.Stream(device=dev)
+    for x in (xa, xb, xa):
+        seeds, geo = r.run(x, side)
+        side.synchronize()
+        ref_seeds, ref_geo = geodesic_guidance(x, 64, 16, 0.5, 20)
+        assert torch.equal(seeds, ref_seeds) and torch.equal(geo, ref_geo)
+        assert torch.equal(r.row_max, ref_geo.max(dim=1).values)
+    assert r.launches_per_run == 17
+
+
 def test_row_max_by_product(oracle_lib, dev):
     """The propagation can hand out the maximum of every row (what both epilogues start from); it must be
     exactly geo.max(dim=1), also for rows that stay empty, and the mask-head epilogue fed with it must
