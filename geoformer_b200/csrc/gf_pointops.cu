@@ -78,7 +78,11 @@ __global__ void group_points_grad_kernel(const float *__restrict__ grad_out, con
 // warps of the CTA; each warp tests 32 points per step (ascending index), orders the hits with a
 // ballot + popc prefix and stops scanning once it holds nsample of them.  The final row equals the
 // reference's: hits in ascending order, the tail padded with the first hit, zeros if no hit.
-constexpr int BQ_WARPS = 16;
+// A warp's scan is one dependent chain per step (shared-memory load -> distance -> vote), so a step covers
+// four 32-point groups whose chains overlap (the hits are still committed group by group, in index order);
+// 8 warps per CTA so that 2048 centres make 256 CTAs (> 148 SMs).
+constexpr int BQ_WARPS = 8;
+constexpr int BQ_GROUPS = 4;
 constexpr int BQ_TILE = 2048;
 
 __global__ void __launch_bounds__(BQ_WARPS * 32)
@@ -112,19 +116,25 @@ __global__ void __launch_bounds__(BQ_WARPS * 32)
       }
       __syncthreads();
       if (!done) {
-        for (int o = 0; o < tn && cnt < nsample; o += 32) {
-          int t = o + lane;
-          bool hit = false;
-          if (t < tn) {
-            float d2 = sq3(cx - sx[t], cy - sy[t], cz - sz[t]);
-            hit = d2 < r2;
+        for (int o = 0; o < tn && cnt < nsample; o += 32 * BQ_GROUPS) {
+          bool hit[BQ_GROUPS];
+          unsigned ball[BQ_GROUPS];
+#pragma unroll
+          for (int u = 0; u < BQ_GROUPS; ++u) {
+            const int t = o + 32 * u + lane;
+            hit[u] = false;
+            if (t < tn) hit[u] = sq3(cx - sx[t], cy - sy[t], cz - sz[t]) < r2;
           }
-          unsigned ball = __ballot_sync(0xffffffffu, hit);
-          if (ball) {
-            if (cnt == 0) first = base + o + __ffs(ball) - 1;
-            int pos = cnt + __popc(ball & ((1u << lane) - 1u));
-            if (hit && pos < nsample) row[pos] = base + t;
-            cnt += __popc(ball);
+#pragma unroll
+          for (int u = 0; u < BQ_GROUPS; ++u) ball[u] = __ballot_sync(0xffffffffu, hit[u]);
+#pragma unroll
+          for (int u = 0; u < BQ_GROUPS; ++u) {
+            if (ball[u]) {  // hits beyond nsample fall off through the pos test, exactly as in the one-group loop
+              if (cnt == 0) first = base + o + 32 * u + __ffs(ball[u]) - 1;
+              const int pos = cnt + __popc(ball[u] & ((1u << lane) - 1u));
+              if (hit[u] && pos < nsample) row[pos] = base + o + 32 * u + lane;
+              cnt += __popc(ball[u]);
+            }
           }
         }
         if (cnt >= nsample) done = true;
