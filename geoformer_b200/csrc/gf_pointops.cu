@@ -74,27 +74,31 @@ __global__ void group_points_grad_kernel(const float *__restrict__ grad_out, con
 }
 
 // ---- ball_query (ball_query_gpu.cu:12-47) -------------------------------------------------------
-// One warp per centre.  The point cloud streams through shared memory in tiles shared by the 16
-// warps of the CTA; each warp tests 32 points per step (ascending index), orders the hits with a
-// ballot + popc prefix and stops scanning once it holds nsample of them.  The final row equals the
-// reference's: hits in ascending order, the tail padded with the first hit, zeros if no hit.
-// A warp's scan is one dependent chain per step (shared-memory load -> distance -> vote), so a step covers
-// four 32-point groups whose chains overlap (the hits are still committed group by group, in index order);
-// 8 warps per CTA so that 2048 centres make 256 CTAs (> 148 SMs).
-constexpr int BQ_WARPS = 8;
-constexpr int BQ_GROUPS = 4;
+// The point cloud streams through shared memory in tiles shared by the 16 warps of a CTA.  FOUR warps work
+// on one centre: each takes a quarter of the tile, votes its hits (ballot words kept in registers), the four
+// hit counts meet in shared memory, and every warp then writes its hits behind those of the quarters before
+// it -- so the row still holds the hits in ascending index order, truncated at nsample, the tail padded with
+// the first hit, zeros if there is none (the reference's result).  One warp per centre left only ~14 warps
+// per SM (2048 centres), each a long dependent chain of load -> distance -> vote steps.
+constexpr int BQ_WPC = 4;        // warps per centre
+constexpr int BQ_CENTRES = 4;    // centres per CTA (16 warps: two CTAs per SM at 64 registers)
+constexpr int BQ_WARPS = BQ_WPC * BQ_CENTRES;
 constexpr int BQ_TILE = 2048;
+constexpr int BQ_PART = BQ_TILE / BQ_WPC;  // points of a tile per warp
+constexpr int BQ_STEPS = BQ_PART / 32;
 
 __global__ void __launch_bounds__(BQ_WARPS * 32)
     ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int B, int N, int m,
                       float radius, int nsample, int *__restrict__ idx) {
-  __shared__ float sx[BQ_TILE], sy[BQ_TILE], sz[BQ_TILE];
+  __shared__ float4 sp[BQ_TILE];  // one 16-byte load per candidate
+  __shared__ int s_cnt[BQ_CENTRES][BQ_WPC], s_first[BQ_CENTRES][BQ_WPC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int groups_per_batch = (m + BQ_WARPS - 1) / BQ_WARPS;
+  const int cl = warp / BQ_WPC, part = warp % BQ_WPC;  // centre slot of the CTA, quarter of the tile
+  const int groups_per_batch = (m + BQ_CENTRES - 1) / BQ_CENTRES;
   const float r2 = __fmul_rn(radius, radius);
   for (int g = blockIdx.x; g < B * groups_per_batch; g += gridDim.x) {
     const int b = g / groups_per_batch;
-    const int j = (g - b * groups_per_batch) * BQ_WARPS + warp;
+    const int j = (g - b * groups_per_batch) * BQ_CENTRES + cl;
     const bool live = j < m;
     const float *P = xyz + (long long)b * N * 3;
     float cx = 0.f, cy = 0.f, cz = 0.f;
@@ -104,46 +108,63 @@ __global__ void __launch_bounds__(BQ_WARPS * 32)
       cx = c[0], cy = c[1], cz = c[2];
       row = idx + ((long long)b * m + j) * nsample;
     }
-    int cnt = 0, first = 0;
+    int cnt = 0, first = -1;  // hits of this centre so far (same value in its four warps), its first hit
     bool done = !live;
     for (int base = 0; base < N; base += BQ_TILE) {
       const int tn = min(BQ_TILE, N - base);
       __syncthreads();  // previous tile fully consumed
-      for (int t = threadIdx.x; t < tn * 3; t += blockDim.x) {
-        float v = __ldg(P + (long long)base * 3 + t);
-        int pt = t / 3, ax = t - pt * 3;
-        (ax == 0 ? sx : ax == 1 ? sy : sz)[pt] = v;
+      for (int t = threadIdx.x; t < tn; t += blockDim.x) {  // one point per thread and pass: no index arithmetic
+        const float *q = P + ((long long)base + t) * 3;
+        sp[t] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
       }
       __syncthreads();
+      unsigned ball[BQ_STEPS];
+      int mine = 0, myfirst = -1;
       if (!done) {
-        for (int o = 0; o < tn && cnt < nsample; o += 32 * BQ_GROUPS) {
-          bool hit[BQ_GROUPS];
-          unsigned ball[BQ_GROUPS];
 #pragma unroll
-          for (int u = 0; u < BQ_GROUPS; ++u) {
-            const int t = o + 32 * u + lane;
-            hit[u] = false;
-            if (t < tn) hit[u] = sq3(cx - sx[t], cy - sy[t], cz - sz[t]) < r2;
+        for (int u = 0; u < BQ_STEPS; ++u) {
+          const int t = part * BQ_PART + 32 * u + lane;
+          bool hit = false;
+          if (t < tn) {
+            const float4 c = sp[t];
+            hit = sq3(cx - c.x, cy - c.y, cz - c.z) < r2;
           }
+          ball[u] = __ballot_sync(0xffffffffu, hit);
+        }
 #pragma unroll
-          for (int u = 0; u < BQ_GROUPS; ++u) ball[u] = __ballot_sync(0xffffffffu, hit[u]);
+        for (int u = 0; u < BQ_STEPS; ++u) mine += __popc(ball[u]);
+        if (first < 0 && mine > 0) {  // the centre's first hit is only needed once
 #pragma unroll
-          for (int u = 0; u < BQ_GROUPS; ++u) {
-            if (ball[u]) {  // hits beyond nsample fall off through the pos test, exactly as in the one-group loop
-              if (cnt == 0) first = base + o + 32 * u + __ffs(ball[u]) - 1;
-              const int pos = cnt + __popc(ball[u] & ((1u << lane) - 1u));
-              if (hit[u] && pos < nsample) row[pos] = base + o + 32 * u + lane;
-              cnt += __popc(ball[u]);
-            }
+          for (int u = BQ_STEPS - 1; u >= 0; --u)
+            if (ball[u]) myfirst = base + part * BQ_PART + 32 * u + __ffs(ball[u]) - 1;
+        }
+      }
+      if (lane == 0) s_cnt[cl][part] = mine, s_first[cl][part] = myfirst;
+      __syncthreads();
+      if (!done) {
+        int before = cnt;  // hits of the earlier quarters of this tile come first
+#pragma unroll
+        for (int q = 0; q < BQ_WPC; ++q) {
+          const int c = s_cnt[cl][q];
+          if (first < 0 && c > 0) first = s_first[cl][q];
+          if (q < part) before += c;
+          cnt += c;
+        }
+        if (mine > 0 && before < nsample) {
+#pragma unroll
+          for (int u = 0; u < BQ_STEPS; ++u) {
+            const int pos = before + __popc(ball[u] & ((1u << lane) - 1u));
+            if (((ball[u] >> lane) & 1u) && pos < nsample) row[pos] = base + part * BQ_PART + 32 * u + lane;
+            before += __popc(ball[u]);
           }
         }
         if (cnt >= nsample) done = true;
       }
       if (__syncthreads_and(done)) break;
     }
-    if (live) {
+    if (live && part == 0) {
       if (cnt > nsample) cnt = nsample;
-      int fill = cnt > 0 ? first : 0;  // ball_query.cpp:22-24 zero-init when nothing is in range
+      const int fill = cnt > 0 ? first : 0;  // ball_query.cpp:22-24 zero-init when nothing is in range
       for (int l = cnt + lane; l < nsample; l += 32) row[l] = fill;
     }
   }
@@ -299,7 +320,7 @@ extern "C" int gf_ball_query(const float *new_xyz, const float *xyz, int B, int 
   GF_CHECK_ARG(B >= 0 && N >= 0 && m >= 0 && nsample >= 0, "ball_query: negative size");
   if ((long long)B * m * nsample == 0) return GF_OK;
   GF_CHECK_ARG(new_xyz && idx && (xyz || N == 0), "ball_query: null pointer");
-  long long groups = (long long)B * ((m + BQ_WARPS - 1) / BQ_WARPS);
+  long long groups = (long long)B * ((m + BQ_CENTRES - 1) / BQ_CENTRES);
   int grid = (int)(groups < (long long)num_sms() * 8 ? groups : (long long)num_sms() * 8);
   ball_query_kernel<<<grid, BQ_WARPS * 32, 0, (cudaStream_t)stream>>>(new_xyz, xyz, B, N, m, radius, nsample, idx);
   GF_LAUNCHED();
