@@ -14,6 +14,8 @@
 //   algo 1  brute-force tiled scan (shared-memory tiles, register-resident sorted top-k).  This
 //           is the formulation named in BASELINE.json; kept as an independent cross-check.
 // 3-D coordinates make this a compare/select problem, not a contraction: no tensor cores.
+#include <stdlib.h>
+
 #include "gf_knn.cuh"
 
 namespace gf {
@@ -439,7 +441,13 @@ int knn_grid_build(const float *xyz, int N, int k, void *workspace, size_t works
     return GF_ERR_WORKSPACE;
   }
   const int nb = num_sms() * 8;
-  const float tau = fmaxf(2.f, 0.45f * (float)k);
+  static float tau_mul = -1.f;  // GF_KNN_TAU: experiment knob for the target cell occupancy (x k)
+  if (tau_mul < 0.f) {
+    const char *e = getenv("GF_KNN_TAU");
+    tau_mul = e ? (float)atof(e) : 0.45f;
+    if (!(tau_mul > 0.f)) tau_mul = 0.45f;
+  }
+  const float tau = fmaxf(2.f, tau_mul * (float)k);
   knn_init_kernel<<<1, 1, 0, st>>>(g, tau);
   GF_LAUNCHED();
   knn_bbox_kernel<<<min(nb, (N + 255) / 256), 256, 0, st>>>(xyz, N, g);
