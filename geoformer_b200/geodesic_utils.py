@@ -119,7 +119,7 @@ def geodesic_from_graph(D, I, seeds, radius, max_step, return_stats=False, row_m
 
 
 def geodesic_from_points(locs, seeds, neighbor, radius, max_step, return_graph=False, return_stats=False,
-                         row_max=None):
+                         row_max=None, ws_tag="guidance"):
     """kNN graph + propagation of one scene in one library call (the body of the reference loop,
     geodesic_utils.py:98-163)."""
     C.check_cuda_f32(locs, "locs")
@@ -133,7 +133,7 @@ def geodesic_from_points(locs, seeds, neighbor, radius, max_step, return_graph=F
     L = C.lib()
     with torch.cuda.device(locs.device):
         nbytes = L.gf_guidance_workspace_bytes(N, Q, int(neighbor))
-        ws = C.workspace.get(locs.device, "guidance", nbytes)
+        ws = C.workspace.get(locs.device, ws_tag, nbytes)
         C.check(L.gf_guidance_seeded(C.ptr(locs), N, C.ptr(seeds), Q, int(neighbor), ctypes.c_float(float(radius)),
                                      int(max_step), C.ptr(geo), C.ptr(D), C.ptr(I), C.ptr(stats), C.ptr(row_max),
                                      C.ptr(ws), nbytes, C.stream_of(locs.device)), "guidance_seeded")
@@ -157,18 +157,55 @@ def cal_geodesic_vectorize(gpu_index, pre_enc_inds, locs_float_, batch_offset_, 
     batch_size = pre_enc_inds.shape[0]
     offsets = batch_offset_.tolist() if isinstance(batch_offset_, torch.Tensor) else list(batch_offset_)
     own_index = gpu_index is None or isinstance(gpu_index, FlatL2Index)
+    fused = own_index and (gpu_index is None or gpu_index.algo == 0)
+    dev = locs_float_.device
+    # The scenes of a batch are independent (the reference loops over them, :98).  On the fused path they are
+    # spread over a few side streams so that one scene's latency-bound stages (the kNN grid build, a
+    # single wave of per-seed propagation CTAs) run under another scene's kernels: ~0.33 instead of ~0.55 ms
+    # per 100k-point scene.  Everything is joined back into the caller's stream before returning.
+    lanes = _side_streams(dev, min(batch_size, _MAX_SCENES_IN_FLIGHT)) if fused and batch_size > 1 and dev.type == "cuda" else []
+    cur = torch.cuda.current_stream(dev) if lanes else None
+    if lanes:
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for st in lanes:
+            st.wait_event(fork)
     geo_dists = []
     for b in range(batch_size):
         start, end = int(offsets[b]), int(offsets[b + 1])
         seeds = pre_enc_inds[b][:n_queries]
         locs_b = locs_float_[start:end].contiguous()
         if end - start == 0:
-            geo_dists.append(torch.empty((seeds.numel(), 0), dtype=torch.float32, device=locs_float_.device))
+            geo_dists.append(torch.empty((seeds.numel(), 0), dtype=torch.float32, device=dev))
             continue
-        if own_index and (gpu_index is None or gpu_index.algo == 0):
+        if fused and lanes:
+            st = lanes[b % len(lanes)]
+            with torch.cuda.stream(st):
+                geo = geodesic_from_points(locs_b, seeds, neighbor, radius, max_step, ws_tag="guidance/lane%d" % (b % len(lanes)))
+            geo.record_stream(cur)  # allocated on the side stream, handed to the caller's
+            locs_b.record_stream(st)
+            seeds.record_stream(st)
+        elif fused:
             geo = geodesic_from_points(locs_b, seeds, neighbor, radius, max_step)
         else:
             D, I = find_knn(gpu_index, locs_b, neighbor=neighbor)
             geo = geodesic_from_graph(D, I, seeds, radius, max_step)
         geo_dists.append(geo)
+    for st in lanes:
+        join = torch.cuda.Event()
+        join.record(st)
+        cur.wait_event(join)
     return geo_dists
+
+
+_MAX_SCENES_IN_FLIGHT = 4
+_lane_streams = {}
+
+
+def _side_streams(device, n):
+    """up to n cached side streams of `device` (created once per device and thread of first use)"""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    have = _lane_streams.setdefault(key, [])
+    while len(have) < n:
+        have.append(torch.cuda.Stream(device=device))
+    return have[:n]

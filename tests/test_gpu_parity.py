@@ -336,6 +336,38 @@ def test_cal_geodesic_vectorize_batch_api(oracle_lib, dev):
         assert np.array_equal(o.cpu().numpy(), r)
 
 
+def test_cal_geodesic_vectorize_batch_overlaps_scenes_and_stays_exact(dev):
+    """A batch of 8 scenes runs on side streams inside cal_geodesic_vectorize: every map must equal the
+    one-scene-at-a-time result, repeatedly (stream / workspace hazards would show up as differences), also
+    when the caller consumes the result on its own non-default stream right away."""
+    from geoformer_b200.geodesic_utils import cal_geodesic_vectorize, geodesic_from_points
+
+    sizes = [20000, 35000, 1, 27000, 31000, 0, 22000, 40000]
+    pts = [scene(n, 70 + i) if n > 50 else torch.zeros(n, 3) for i, n in enumerate(sizes)]
+    locs = torch.cat(pts).to(dev)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    Q = 32
+    gen = torch.Generator().manual_seed(3)
+    pre = torch.stack([torch.randint(0, max(n, 1), (48,), generator=gen) for n in sizes]).int().to(dev)
+    singles = []
+    for b, n in enumerate(sizes):
+        lb = locs[int(offs[b]):int(offs[b + 1])].contiguous()
+        singles.append(geodesic_from_points(lb, pre[b][:Q], 16, 0.5, 24) if n > 0 else None)
+    torch.cuda.synchronize()
+    user = torch.cuda.Stream(device=dev)
+    for rep in range(3):
+        with torch.cuda.stream(user):
+            out = cal_geodesic_vectorize(None, pre, locs, torch.from_numpy(offs).to(dev), max_step=24, neighbor=16,
+                                         radius=0.5, n_queries=Q)
+            sums = [o.sum() if o.numel() else None for o in out]  # consumed on the caller's stream at once
+        user.synchronize()
+        for b, n in enumerate(sizes):
+            assert out[b].shape == (Q, n)
+            if n > 0:
+                assert torch.equal(out[b], singles[b]), (rep, b)
+                assert torch.equal(sums[b], singles[b].sum())
+
+
 def test_full_size_config_c2(oracle_lib, dev):
     """BASELINE config 2 at full size (100k points, 256 seeds, k=16, radius 0.5, 32 levels) through the
     fused entry point: seeds == oracle FPS; kNN rows == oracle on a 2000-row sample (and grid == brute
