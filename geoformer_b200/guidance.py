@@ -13,7 +13,7 @@ from . import _capi as C
 
 
 def geodesic_guidance(xyz, n_queries, neighbor, radius, max_step, return_graph=False, return_stats=False,
-                      row_max=None):
+                      row_max=None, ws_tag="guidance"):
     """xyz (N,3) f32 CUDA -> (seeds (Q,) i32, geo (Q,N) f32 [, D (N,k) f32, I (N,k) i32][, stats (2,) i64]).
     row_max: optional (Q,) f32 CUDA tensor that receives the maximum of every row of geo (for the epilogues)."""
     C.check_cuda_f32(xyz, "xyz")
@@ -28,7 +28,7 @@ def geodesic_guidance(xyz, n_queries, neighbor, radius, max_step, return_graph=F
     L = C.lib()
     with torch.cuda.device(dev):
         nbytes = L.gf_guidance_workspace_bytes(N, Q, k)
-        ws = C.workspace.get(dev, "guidance", nbytes)
+        ws = C.workspace.get(dev, ws_tag, nbytes)
         C.check(L.gf_guidance(C.ptr(xyz), N, Q, k, ctypes.c_float(float(radius)), int(max_step), C.ptr(seeds),
                               C.ptr(geo), C.ptr(D), C.ptr(I), C.ptr(stats), C.ptr(row_max), C.ptr(ws), nbytes,
                               C.stream_of(dev)), "guidance")
