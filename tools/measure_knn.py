@@ -12,4 +12,4 @@ def t(fn, reps=10):
     return a.elapsed_time(b) / reps
 for name, x in (("c2", scene(100_000, 1234).to(dev)), ("c1", scene(50_000, 1234).to(dev)), ("c4", room(1_000_000, 4321).to(dev))):
     for k in (8, 16, 32):
-        print(os.environ.get("GF_KNN_QUERY", "warp"), name, "k", k, "knn ms %.4f" % t(lambda: knn_graph(x, k, index_dtype=torch.int32)))
+        print("tau", os.environ.get("GF_KNN_TAU", "0.45"), name, "k", k, "knn ms %.4f" % t(lambda: knn_graph(x, k, index_dtype=torch.int32)))
