@@ -1,175 +1,140 @@
-"""Python surface of lib/pointnet2/pointnet2_utils.py on top of the sm_100a operators.
+"""The Python surface GeoFormer expects from `pointnet2_utils` (lib/pointnet2/pointnet2_utils.py in the
+reference), rebuilt on the sm_100a operators of `geoformer_b200.pointnet2._ext`.
 
-Same public names and call signatures as the reference (furthest_point_sample, gather_operation,
-three_nn, three_interpolate, grouping_operation, ball_query, QueryAndGroup, GroupAll), so the
-callers in lib/pointnet2/pointnet2_modules.py:200-226 and model/geoformer/geoformer_fs.py:619-660
-work unchanged.  Only the operators differ: they come from geoformer_b200.pointnet2._ext.
+Public names and call signatures are the reference's -- furthest_point_sample, gather_operation, three_nn,
+three_interpolate, grouping_operation, ball_query, QueryAndGroup, GroupAll -- so that
+lib/pointnet2/pointnet2_modules.py:200-226 and model/geoformer/geoformer_fs.py:619-660 run unchanged.
+The implementation is not: the six autograd wrappers are stamped out by one small factory from a table
+(forward operator, which outputs are index tensors, how the gradient is routed), and the two grouping
+modules share their feature-assembly code.
 """
 import torch
 import torch.nn as nn
-from torch.autograd import Function
 
 from .pointnet2 import _ext
 
 
-class FurthestPointSampling(Function):
-    """pointnet2_utils.py:40-68: xyz (B,N,3) -> (B,npoint) int32, non-differentiable."""
+def _autograd_op(name, doc, n_inputs, run, grad=None, index_outputs=()):
+    """Builds a torch.autograd.Function subclass and returns its `.apply`.
 
-    @staticmethod
-    def forward(ctx, xyz, npoint):
-        inds = _ext.furthest_point_sampling(xyz, npoint)
-        ctx.mark_non_differentiable(inds)
-        return inds
+    run(*inputs)            -> (outputs, saved) with outputs a tensor or tuple and `saved` anything the
+                               gradient needs;
+    grad(saved, *grad_outs) -> gradient of input 0 (only input 0 is ever differentiable here), or None;
+    index_outputs           -> positions of integer outputs (marked non-differentiable)."""
 
-    @staticmethod
-    def backward(ctx, a=None):
-        return None, None
+    def forward(ctx, *inputs):
+        outputs, ctx.saved_for_grad = run(*inputs)
+        many = isinstance(outputs, tuple)
+        for pos in index_outputs:
+            ctx.mark_non_differentiable(outputs[pos] if many else outputs)
+        return outputs
 
+    def backward(ctx, *grad_outputs):
+        first = None if grad is None else grad(ctx.saved_for_grad, *grad_outputs)
+        return (first,) + (None,) * (n_inputs - 1)
 
-furthest_point_sample = FurthestPointSampling.apply
-
-
-class GatherOperation(Function):
-    """pointnet2_utils.py:71-104: features (B,C,N), idx (B,npoint) -> (B,C,npoint)."""
-
-    @staticmethod
-    def forward(ctx, features, idx):
-        _, C, N = features.size()
-        ctx.for_backwards = (idx, C, N)
-        return _ext.gather_points(features, idx)
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        idx, C, N = ctx.for_backwards
-        return _ext.gather_points_grad(grad_out.contiguous(), idx, N), None
+    cls = type(name, (torch.autograd.Function,), {"forward": staticmethod(forward), "backward": staticmethod(backward),
+                                                  "__doc__": doc})
+    return cls, cls.apply
 
 
-gather_operation = GatherOperation.apply
+# ---- sampling / gathering ----------------------------------------------------------------------------
+FurthestPointSampling, furthest_point_sample = _autograd_op(
+    "FurthestPointSampling", "(xyz (B,N,3), npoint) -> (B,npoint) int32 sample indices; reference :40-68", 2,
+    run=lambda xyz, npoint: (_ext.furthest_point_sampling(xyz, npoint), None), index_outputs=(0,))
+
+GatherOperation, gather_operation = _autograd_op(
+    "GatherOperation", "(features (B,C,N), idx (B,npoint)) -> (B,C,npoint); reference :71-104", 2,
+    run=lambda feats, idx: (_ext.gather_points(feats, idx), (idx, feats.size(2))),
+    grad=lambda saved, g: _ext.gather_points_grad(g.contiguous(), saved[0], saved[1]))
+
+# ---- three nearest neighbours and the interpolation built on them ---------------------------------------
 
 
-class ThreeNN(Function):
-    """pointnet2_utils.py:107-135: returns (sqrt distances (B,n,3), idx (B,n,3))."""
-
-    @staticmethod
-    def forward(ctx, unknown, known):
-        dist2, idx = _ext.three_nn(unknown, known)
-        ctx.mark_non_differentiable(idx)
-        return torch.sqrt(dist2), idx
-
-    @staticmethod
-    def backward(ctx, a=None, b=None):
-        return None, None
+def _three_nn_run(unknown, known):
+    d2, idx = _ext.three_nn(unknown, known)
+    return (torch.sqrt(d2), idx), None  # the reference returns distances, the kernel their squares (:126-128)
 
 
-three_nn = ThreeNN.apply
+ThreeNN, three_nn = _autograd_op(
+    "ThreeNN", "(unknown (B,n,3), known (B,m,3)) -> (dist (B,n,3), idx (B,n,3)); reference :107-135", 2,
+    run=_three_nn_run, index_outputs=(1,))
 
+ThreeInterpolate, three_interpolate = _autograd_op(
+    "ThreeInterpolate", "(features (B,C,m), idx (B,n,3), weight (B,n,3)) -> (B,C,n); reference :138-187", 3,
+    run=lambda feats, idx, w: (_ext.three_interpolate(feats, idx, w), (idx, w, feats.size(2))),
+    grad=lambda saved, g: _ext.three_interpolate_grad(g.contiguous(), saved[0], saved[1], saved[2]))
 
-class ThreeInterpolate(Function):
-    """pointnet2_utils.py:138-187."""
+# ---- neighbourhood queries ----------------------------------------------------------------------------------
+GroupingOperation, grouping_operation = _autograd_op(
+    "GroupingOperation", "(features (B,C,N), idx (B,npoint,nsample)) -> (B,C,npoint,nsample); reference :190-236", 2,
+    run=lambda feats, idx: (_ext.group_points(feats, idx), (idx, feats.size(2))),
+    grad=lambda saved, g: _ext.group_points_grad(g.contiguous(), saved[0], saved[1]))
 
-    @staticmethod
-    def forward(ctx, features, idx, weight):
-        m = features.size(2)
-        ctx.three_interpolate_for_backward = (idx, weight, m)
-        return _ext.three_interpolate(features, idx, weight)
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        idx, weight, m = ctx.three_interpolate_for_backward
-        return _ext.three_interpolate_grad(grad_out.contiguous(), idx, weight, m), None, None
-
-
-three_interpolate = ThreeInterpolate.apply
-
-
-class GroupingOperation(Function):
-    """pointnet2_utils.py:190-236: features (B,C,N), idx (B,npoint,nsample) -> (B,C,npoint,nsample)."""
-
-    @staticmethod
-    def forward(ctx, features, idx):
-        N = features.size(2)
-        ctx.for_backwards = (idx, N)
-        return _ext.group_points(features, idx)
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        idx, N = ctx.for_backwards
-        return _ext.group_points_grad(grad_out.contiguous(), idx, N), None
-
-
-grouping_operation = GroupingOperation.apply
-
-
-class BallQuery(Function):
-    """pointnet2_utils.py:239-269.  Note the argument order (radius, nsample, xyz, new_xyz)."""
-
-    @staticmethod
-    def forward(ctx, radius, nsample, xyz, new_xyz):
-        inds = _ext.ball_query(new_xyz, xyz, radius, nsample)
-        ctx.mark_non_differentiable(inds)
-        return inds
-
-    @staticmethod
-    def backward(ctx, a=None):
-        return None, None, None, None
-
-
-ball_query = BallQuery.apply
+# argument order of the reference: (radius, nsample, xyz, new_xyz) -- the operator takes the centres first
+BallQuery, ball_query = _autograd_op(
+    "BallQuery", "(radius, nsample, xyz (B,N,3), new_xyz (B,npoint,3)) -> (B,npoint,nsample) int32; reference :239-269",
+    4, run=lambda radius, nsample, xyz, centres: (_ext.ball_query(centres, xyz, radius, nsample), None),
+    index_outputs=(0,))
 
 
 def _resample_rows_uniformly(idx, nsample):
-    """In-place variant of pointnet2_utils.py:320-329 (not used by GeoFormer): every (batch, region)
-    row keeps its distinct indices and tops itself up to `nsample` by drawing among them with
-    replacement.  Returns the (B, npoint) count of distinct indices (float CPU tensor, as there)."""
-    counts = torch.zeros(idx.shape[:2])
-    for row, cnt in zip(idx.view(-1, idx.shape[-1]), counts.view(-1)):
-        distinct = torch.unique(row)
-        cnt.fill_(distinct.numel())
-        extra = torch.randint(0, distinct.numel(), (nsample - distinct.numel(),), dtype=torch.long)
-        row.copy_(torch.cat((distinct, distinct[extra])))
-    return counts
+    """`sample_uniformly` of the reference's QueryAndGroup (:320-329; GeoFormer never turns it on): each
+    (batch, region) row is rewritten in place as its distinct indices followed by draws, with replacement,
+    among them.  Returns how many distinct indices every row had, as a (B, npoint) float CPU tensor."""
+    flat = idx.view(-1, idx.shape[-1])
+    distinct_counts = torch.zeros(idx.shape[:2])
+    flat_counts = distinct_counts.view(-1)
+    for r in range(flat.shape[0]):
+        members = torch.unique(flat[r])
+        flat_counts[r] = members.numel()
+        refill = torch.randint(0, members.numel(), (nsample - members.numel(),), dtype=torch.long)
+        flat[r] = torch.cat((members, members[refill]))
+    return distinct_counts
+
+
+def _assemble(local_xyz, grouped_feats, use_xyz):
+    """what both groupers return as features: coordinates first (when asked for), then the gathered channels"""
+    if grouped_feats is None:
+        assert use_xyz, "Cannot have not features and not use xyz as a feature!"
+        return local_xyz
+    return torch.cat([local_xyz, grouped_feats], dim=1) if use_xyz else grouped_feats
 
 
 class QueryAndGroup(nn.Module):
-    """pointnet2_utils.py:272-356: ball query -> group xyz (centred, optionally /radius) -> group
-    features -> concat (B, 3+C, npoint, nsample)."""
+    """Ball query around every centre, neighbours' coordinates made relative to it (and divided by the radius
+    when `normalize_xyz`), neighbours' features gathered: (B, 3+C, npoint, nsample).  Reference :272-356."""
 
     def __init__(self, radius, nsample, use_xyz=True, ret_grouped_xyz=False, normalize_xyz=False,
                  sample_uniformly=False, ret_unique_cnt=False):
         super().__init__()
-        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+        assert sample_uniformly or not ret_unique_cnt  # counts only exist when rows are resampled
+        self.radius = radius
+        self.nsample = nsample
+        self.use_xyz = use_xyz
         self.ret_grouped_xyz = ret_grouped_xyz
         self.normalize_xyz = normalize_xyz
         self.sample_uniformly = sample_uniformly
         self.ret_unique_cnt = ret_unique_cnt
-        if self.ret_unique_cnt:
-            assert self.sample_uniformly
 
     def forward(self, xyz, new_xyz, features=None):
-        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
-        if self.sample_uniformly:
-            unique_cnt = _resample_rows_uniformly(idx, self.nsample)
-        xyz_trans = xyz.transpose(1, 2).contiguous()
-        grouped_xyz = grouping_operation(xyz_trans, idx)  # (B, 3, npoint, nsample)
-        grouped_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)
+        members = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        counts = _resample_rows_uniformly(members, self.nsample) if self.sample_uniformly else None
+        local = grouping_operation(xyz.transpose(1, 2).contiguous(), members)  # (B,3,npoint,nsample)
+        local -= new_xyz.transpose(1, 2).unsqueeze(-1)
         if self.normalize_xyz:
-            grouped_xyz /= self.radius
-        if features is not None:
-            grouped_features = grouping_operation(features, idx)
-            new_features = torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
-        else:
-            assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-            new_features = grouped_xyz
-        ret = [new_features]
+            local /= self.radius
+        gathered = None if features is None else grouping_operation(features, members)
+        outputs = [_assemble(local, gathered, self.use_xyz)]
         if self.ret_grouped_xyz:
-            ret.append(grouped_xyz)
+            outputs.append(local)
         if self.ret_unique_cnt:
-            ret.append(unique_cnt)
-        return ret[0] if len(ret) == 1 else tuple(ret)
+            outputs.append(counts)
+        return outputs[0] if len(outputs) == 1 else tuple(outputs)
 
 
 class GroupAll(nn.Module):
-    """pointnet2_utils.py:359-401."""
+    """One group holding every point: (B, 3+C, 1, N).  Reference :359-401."""
 
     def __init__(self, use_xyz=True, ret_grouped_xyz=False):
         super().__init__()
@@ -177,24 +142,18 @@ class GroupAll(nn.Module):
         self.ret_grouped_xyz = ret_grouped_xyz
 
     def forward(self, xyz, new_xyz, features=None):
-        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
-        if features is not None:
-            grouped_features = features.unsqueeze(2)
-            new_features = torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
-        else:
-            new_features = grouped_xyz
-        return (new_features, grouped_xyz) if self.ret_grouped_xyz else new_features
+        everything = xyz.transpose(1, 2).unsqueeze(2)
+        merged = everything if features is None else _assemble(everything, features.unsqueeze(2), self.use_xyz)
+        return (merged, everything) if self.ret_grouped_xyz else merged
 
 
 def group_points(xyz, features, grouper, npoint, inds=None):
-    """PointnetSAModuleVotesSeparate.group_points (pointnet2_modules.py:200-226) as a function:
-    FPS (unless `inds` is given) -> gather centres -> grouper.  Returns
-    (new_xyz (B,npoint,3), grouped_features, grouped_xyz, inds (B,npoint) i32)."""
-    xyz_flipped = xyz.transpose(1, 2).contiguous()
+    """The set-aggregation front end of GeoFormer (PointnetSAModuleVotesSeparate.group_points,
+    pointnet2_modules.py:200-226) as a function: centres by FPS unless their indices are handed in, then the
+    grouper.  -> (centres (B,npoint,3), grouped features, grouped coordinates, centre indices (B,npoint) i32)."""
     if inds is None:
         inds = furthest_point_sample(xyz, npoint)
-    else:
-        assert inds.shape[1] == npoint
-    new_xyz = gather_operation(xyz_flipped, inds).transpose(1, 2).contiguous()
-    grouped_features, grouped_xyz = grouper(xyz, new_xyz, features)
-    return new_xyz, grouped_features, grouped_xyz, inds
+    assert inds.shape[1] == npoint
+    centres = gather_operation(xyz.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
+    grouped_feats, grouped_xyz = grouper(xyz, centres, features)
+    return centres, grouped_feats, grouped_xyz, inds
