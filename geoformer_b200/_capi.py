@@ -100,11 +100,18 @@ def reset_launch_count():
 
 # ---- tensor plumbing ------------------------------------------------------------------------------
 def ptr(t):
-    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+    # plain ints / None convert to void* through the declared argtypes; no ctypes object per argument
+    return t.data_ptr() if t is not None else None
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def stream_of(device):
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """the current CUDA stream of `device` as a raw cudaStream_t value"""
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def require(cond, msg):
