@@ -284,6 +284,9 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
         if (BITMAP && rt >= 0 && !rissued) resolve_issue();
 #pragma unroll
         for (int u = 0; u < GEO_UNROLL; ++u) {
+          // slots past the end hold the sentinel (every claim would be rejected): on small frontiers whole
+          // warps skip them instead of running four rejected claims per lane
+          if (u > 0 && n0 + u * (int)ngroups >= Fs) continue;
           const uint32_t key = keybase | (pl[u] << 2);
           geo_claim4<MODE>(key, t[u], N, level, vis, clm, rowu, nq, ovf, &s_next_n[level & 1]);
         }
