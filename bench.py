@@ -231,6 +231,28 @@ def config_block(cfg, args, extra=None):
     return c
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-rank runs only: keep this rank's host threads (and therefore the first-touch placement of its
+    pinned buffers) on the CPUs NVML reports as local to its GPU, so that several ranks' D2H copies do not
+    all land in one socket's memory.  Best effort: any failure leaves the affinity as it was."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w in range(len(mask)) for b in range(64) if (int(mask[w]) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if len(cpus) >= 4:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------
 def run_seed_sharded(args):
     """One scene, seed blocks per rank (strong scaling).  Not the driver's default line: an extra mode
@@ -316,6 +338,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
 
@@ -596,7 +619,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stage_ms": stage_ms, "stage_ms_serial": stage_ms_serial, "epilogues": epilogues,
             "eval_setting_max_step_256": eval_setting, "scenes_per_s": value / Q,
-            "host_enqueue_ms_per_step": host_enqueue_ms,
+            "host_enqueue_ms_per_step": host_enqueue_ms, "host_cpus_bound_to_gpu_node": numa_cpus,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
