@@ -460,7 +460,8 @@ static FpsPlan plan_fps(int N, int max_cs) {
     if ((long long)cs * 256 * kFpsP256[pi] >= N) return {256, kFpsP256[pi], cs};
   if ((long long)max_cs * 512 * 24 >= N) return {512, 24, max_cs};
   // beyond one cluster: one CTA per SM, registers if the scene fits (P <= 32), else streaming from L2
-  const int ctas = num_sms() & ~1;  // even, so that CTAs * 256 covers whole sets of 512 residue classes
+  int ctas = num_sms() & ~1;  // even, so that CTAs * 256 covers whole sets of 512 residue classes
+  if (ctas > FPS_MAX_GRID_CTAS) ctas = FPS_MAX_GRID_CTAS;  // what launch_fps_grid launches
   const int p_opts[4] = {8, 16, 24, 32};
   for (int pi = 0; pi < 4; ++pi)
     if ((long long)ctas * FPS_GRID_T * p_opts[pi] >= N) return {FPS_GRID_T, p_opts[pi], 0};
