@@ -11,7 +11,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgeoformer_b200.so")
+# GF_LIB: development builds of the same library (python -m geoformer_b200.build --variant=trace -DGF_TRACE)
+LIB_PATH = os.environ.get("GF_LIB") or os.path.join(_HERE, "libgeoformer_b200.so")
 
 _lib = None
 _lock = threading.Lock()
@@ -51,6 +52,8 @@ SIGNATURES = {
     "gf_guidance_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gf_guidance": (c_int, [_P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gf_guidance_seeded": (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gf_guidance_batch_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
+    "gf_guidance_batch": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "gf_geodesic_scatter": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_int, _P, _P, c_int, _P, _P,
                                     c_size_t, _P]),
     "gf_guidance_seeded_scatter": (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, c_int, _P, _P,

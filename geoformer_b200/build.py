@@ -39,7 +39,13 @@ def _newest_header():
     return max(os.path.getmtime(h) for h in hs)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, extra=()):
+    """variant: development builds (e.g. -DGF_TRACE) go to libgeoformer_b200_<variant>.so with their own object
+    directory; GF_LIB=<path> makes geoformer_b200._capi load one of them instead of the product library."""
+    global OBJ, LIB
+    if variant:
+        OBJ = os.path.join(HERE, "build", variant)
+        LIB = os.path.join(HERE, "libgeoformer_b200_%s.so" % variant)
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     hdr = _newest_header()
@@ -52,7 +58,8 @@ def build(force=False, verbose=False):
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
                 and os.path.getmtime(obj) > hdr):
             return obj, ""
-        cmd = [_nvcc()] + ccbin + NVCC_FLAGS + os.environ.get("GF_NVCC_EXTRA", "").split() + ["-c", src, "-o", obj]
+        cmd = ([_nvcc()] + ccbin + NVCC_FLAGS + os.environ.get("GF_NVCC_EXTRA", "").split() + list(extra)
+               + ["-c", src, "-o", obj])
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -76,4 +83,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    ext = [a for a in sys.argv[1:] if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=var[0] if var else None, extra=ext))

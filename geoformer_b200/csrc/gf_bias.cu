@@ -106,17 +106,24 @@ __global__ void __launch_bounds__(256)
       n2 = __fmul_rn(__fdiv_rn(__fsub_rn(v2, mn2), df2), two_pi);
     }
     const int nc = min(32, C - c0);
-    for (int j = (int)lane; j < d_out; j += 32) {
-      const float b0 = __ldg(gauss_B + j), b1 = __ldg(gauss_B + ldb + j), b2 = __ldg(gauss_B + 2 * ldb + j);
+    // warp-uniform trip count: every lane takes part in the shuffles of every round, lanes whose frequency
+    // j is past d_out (d_out < 32 or not a multiple of 32) only skip the loads and the stores
+    for (int jb = 0; jb < d_out; jb += 32) {
+      const int j = jb + (int)lane;
+      const bool live = j < d_out;
+      const float b0 = live ? __ldg(gauss_B + j) : 0.f, b1 = live ? __ldg(gauss_B + ldb + j) : 0.f,
+                  b2 = live ? __ldg(gauss_B + 2 * ldb + j) : 0.f;
       float *o = out + ((size_t)q * C + c0) * d_pos + j;
       for (int i = 0; i < nc; ++i) {
         const float x0 = __shfl_sync(0xffffffffu, n0, i), x1 = __shfl_sync(0xffffffffu, n1, i),
                     x2 = __shfl_sync(0xffffffffu, n2, i);
-        const float p = fmaf(x2, b2, fmaf(x1, b1, __fmul_rn(x0, b0)));
-        float sn, cs;
-        sincosf(p, &sn, &cs);
-        __stcs(o + (size_t)i * d_pos, sn);
-        __stcs(o + (size_t)i * d_pos + d_out, cs);
+        if (live) {
+          const float p = fmaf(x2, b2, fmaf(x1, b1, __fmul_rn(x0, b0)));
+          float sn, cs;
+          sincosf(p, &sn, &cs);
+          __stcs(o + (size_t)i * d_pos, sn);
+          __stcs(o + (size_t)i * d_pos + d_out, cs);
+        }
       }
     }
   }

@@ -23,7 +23,15 @@ static thread_local bool g_stage_armed = false;
 
 void stage_mark(int stage, cudaStream_t st) {
   if (!g_stage_armed || stage < 0 || stage >= ST_COUNT) return;
-  if (g_stage_ev[stage]) cudaEventRecord(g_stage_ev[stage], st);
+  if (g_stage_ev[stage]) {
+    // inside a stream capture the event becomes an EXTERNAL record node of the graph: every replay stamps it,
+    // and cudaEventElapsedTime between two of them is valid after the replay has finished
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+      cudaEventRecordWithFlags(g_stage_ev[stage], st, cudaEventRecordExternal);
+    else
+      cudaEventRecord(g_stage_ev[stage], st);
+  }
   if (stage == ST_GEO_DONE) g_stage_armed = false;  // one call only
 }
 

@@ -489,13 +489,22 @@ static int launch_fps(const float *xyz, int B, int N, int m, int L, int CS, floa
   cfg.blockDim = dim3(T, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // FPS is the longest dependency chain of the hot path (m - 1 dependent rounds on <= 16 SMs): its cluster should be
+  // placed ahead of queued bulk work.  As a launch attribute the priority also survives stream capture (a graph's
+  // kernel nodes do not inherit the priority of the stream they were captured on).
+  static const int prio_hi = [] {
+    int lo = 0, hi = 0;
+    return cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess ? hi : 0;
+  }();
+  attr[1].id = cudaLaunchAttributePriority;
+  attr[1].val.priority = prio_hi;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   GF_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, L, temp, idx));
   count_launch();
   return GF_OK;

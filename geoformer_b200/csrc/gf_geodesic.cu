@@ -35,6 +35,7 @@
 // epilogues) and, for seed-sharded scenes, the finished row pushed into the peers' matrices over NVLink.
 // History of the formulations that were measured and replaced: DESIGN.md section 4.3.
 #include <stdlib.h>
+#include <string.h>
 
 #include "gf_geodesic.cuh"
 
@@ -63,7 +64,8 @@ struct GeoArgs {
   int n_peers;
   float *peer_geo[GEO_MAX_PEERS];  // row q of this launch goes to peer_geo[r] + q * N
 #ifdef GF_TRACE
-  long long *trace;  // development only: per-level timestamps of CTA 0
+  long long *trace;   // development only: per-seed start / end
+  long long *trace2;  // development only: per-level, per-warp phase timestamps of CTAs 0..3 (streamlined kernel)
 #endif
 };
 
@@ -80,7 +82,8 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
 // lane can fetch four targets with one 16-byte load.
 template <bool IS64>
 __global__ void geo_pack_edges_kernel(const float *__restrict__ D, const void *__restrict__ I, int N, int k,
-                                      float radius, int slot_bits, int *__restrict__ tgt, float *__restrict__ len) {
+                                      float radius, int slot_bits, int enc, int *__restrict__ tgt,
+                                      float *__restrict__ len) {
   const int KP = 1 << slot_bits, K = k - 1;
   const long long total = ((long long)N + 1) << slot_bits;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
@@ -94,7 +97,7 @@ __global__ void geo_pack_edges_kernel(const float *__restrict__ D, const void *_
       const float w = __ldg(D + at);
       if (w <= radius && t >= 0 && t < N) to = (int)t, wo = w;
     }
-    tgt[e] = to;
+    tgt[e] = enc ? (int)(((unsigned)to >> 5) << 7 | ((unsigned)to & 31u)) : to;
     len[e] = wo;
   }
 }
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
     }
 #ifdef GF_TRACE
     __syncthreads();
-    if (tid == 0 && q < 1024) {
+    if (tid == 0 && q < 1024 && a.trace) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t1));
       a.trace[q * 4 + 0] = tr_t0, a.trace[q * 4 + 1] = tr_t1;
       a.trace[q * 4 + 2] = (long long)(reached_total - tr_r0), a.trace[q * 4 + 3] = ((long long)blockIdx.x << 32) | level;
@@ -415,6 +418,300 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
   if (tid == 0) {
     if (reached_total) atomicAdd(a.stats, reached_total);
     atomicMax(a.stats + 1, (unsigned long long)deepest);
+  }
+}
+
+// ---- the batched two-bitmap kernel (scenes whose bitmaps fit on chip: N <~ 860k) -----------------------------
+// Same algorithm and per-seed state as geo_seed_bfs_kernel<2, .>, restated for THROUGHPUT:
+//  * A per-seed run is a chain of dependent latencies (per level: queue -> edge row (L2) -> visited words ->
+//    barrier -> bitmap scan -> counter atomic -> queue, plus three dependent global loads per won point), measured
+//    at 3.5 us per level for a 15-point frontier and 8 us for 800 points with two 1024-thread CTAs per SM -- the SM
+//    issues at ~40 % while its 2048 thread slots are full.  So the work items are (scene, seed) pairs of a whole
+//    BATCH of scenes (the reference's own call is batched: cal_geodesic_vectorize loops over the scenes of a batch,
+//    geodesic_utils.py:98), pulled from one counter by persistent CTAs of 256 / 512 threads, 7 / 4 per SM: three to
+//    four times as many chains in flight per SM, one launch, one tail per batch instead of one per scene.
+//  * Edge targets are stored ENCODED (geo_enc_target) so that the visited test is four instructions.
+//  * The distance of a point won at level L-1 needs three dependent loads (its key, then the edge length and the
+//    parent's distance).  The key load of a thread's first point is issued when level L starts and the other two
+//    after the claims, so the chain runs under the claims instead of after them.
+constexpr int GEO_MAXB = 16;  // scenes per launch (descriptors travel in the kernel parameters)
+
+struct GeoScene {
+  const int *tgt;             // (N + 1, KP) encoded edge targets
+  const float *len;           // (N + 1, KP) edge lengths
+  const int *seeds;           // (Q)
+  float *geo;                 // (Q, N)
+  float *row_max;             // optional (Q)
+  unsigned long long *stats;  // optional: [0] reached pairs, [1] deepest level (device)
+  int N, Q, item0, bitmap_words;
+};
+struct GeoBatchArgs {
+  GeoScene sc[GEO_MAXB];
+  int B, total_items, max_step, slot_bits, qcap;
+  int *overflow;  // per CTA: ovf_stride frontier entries beyond the on-chip queue
+  size_t ovf_stride;
+  unsigned *item_counter;
+#ifdef GF_TRACE
+  long long *trace, *trace2;
+#endif
+};
+
+// ENCODED edge targets: the edge table stores a target t as (t >> 5) << 7 | (t & 31), i.e. the byte offset of its
+// bitmap word shifted left by 5 with the bit number in the low five bits.  The visited test of an edge -- 93 % of
+// the edges of a kNN graph fail it -- is then four instructions (shift, LDS, funnel shift for the bit, LOP3 into a
+// predicate) instead of eight; the byte offset into the output row (4 * t) is only rebuilt on the rare hit.
+// The four visited words are fetched first (independent loads), then tested.
+__device__ __forceinline__ void geo_claim4_enc(uint32_t key, const int4 t, uint32_t vis_s, uint32_t clm_s,
+                                               unsigned char *rowb) {
+  const unsigned tt[4] = {(unsigned)t.x, (unsigned)t.y, (unsigned)t.z, (unsigned)t.w};
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) asm("ld.shared.u32 %0, [%1];" : "=r"(w[e]) : "r"(vis_s + (tt[e] >> 5)));
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const uint32_t bit = __funnelshift_l(0u, 1u, tt[e]);  // 1 << (t & 31)
+    if (!(w[e] & bit)) {
+      const uint32_t boff = (tt[e] & ~127u) | ((tt[e] & 31u) << 2);  // 4 * t
+      // both fire and forget (RED.MIN, ATOMS.OR without a destination)
+      asm volatile("red.relaxed.gpu.global.min.u32 [%0], %1;" ::"l"(rowb + boff), "r"(key + e) : "memory");
+      asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(clm_s + (tt[e] >> 5)), "r"(bit) : "memory");
+    }
+  }
+}
+
+template <int THREADS, int U>
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(const GeoBatchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int *fq = reinterpret_cast<int *>(smem_raw);  // the frontier queue (rebuilt by every commit), a.qcap entries
+  uint32_t *vis = reinterpret_cast<uint32_t *>(fq + a.qcap);
+  __shared__ int s_next_n[2], s_item;  // next-frontier counter, by level parity
+  __shared__ uint32_t s_rmax[THREADS / 32];
+
+  const int QC = a.qcap;
+  const unsigned sb = (unsigned)a.slot_bits, KP = 1u << sb;
+  const unsigned tid = threadIdx.x;
+  const unsigned lsb = sb - 2, sub = tid & ((1u << lsb) - 1u);
+  const unsigned group = tid >> lsb, ngroups = THREADS >> lsb;
+  const uint32_t keybase = GEO_KEYBIT | (sub << 2);
+  int *ovf = a.overflow + (size_t)blockIdx.x * a.ovf_stride;
+  // opaque copies: without them ptxas re-derives these addresses (S2R of the CTA's shared window, constant-bank
+  // loads, 64-bit multiply-adds) inside every claim instead of spending a register on them
+  uint32_t vis_s = (uint32_t)__cvta_generic_to_shared(vis), fq_s = (uint32_t)__cvta_generic_to_shared(fq);
+  asm volatile("mov.u32 %0, %0;" : "+r"(vis_s));
+  asm volatile("mov.u32 %0, %0;" : "+r"(fq_s));
+  auto fq_at = [&](int i) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(fq_s + 4u * (unsigned)i) : "memory");
+    return v;
+  };
+
+  for (;;) {
+    if (tid == 0) s_item = (int)atomicAdd(a.item_counter, 1u);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= a.total_items) break;
+    int b = 0;
+    while (b + 1 < a.B && a.sc[b + 1].item0 <= item) ++b;
+    const GeoScene &S = a.sc[b];
+    const int q = item - S.item0, N = S.N, words = S.bitmap_words;
+    // frontier entry i >= QC lives in the CTA's overflow area: consecutive levels hold disjoint point sets
+    // (F_L + F_{L+1} <= N + 1), so one buffer of N + 2 entries serves both, odd levels from the bottom, even from the top
+    auto ovf_at = [&](int i, int parity) { return parity ? (size_t)(i - QC) : (size_t)N + 1 - (size_t)(i - QC); };
+    auto frontier = [&](int i, int parity) { return i < QC ? fq_at(i) : ovf[ovf_at(i, parity)]; };
+    uint32_t *clm = vis + words;
+    uint32_t clm_s = vis_s + 4u * (uint32_t)words;
+    asm volatile("mov.u32 %0, %0;" : "+r"(clm_s));
+    const int4 *__restrict__ trow = reinterpret_cast<const int4 *>(S.tgt) + sub;  // + (p << lsb)
+    float *row = S.geo + (size_t)q * N;
+    asm volatile("mov.u64 %0, %0;" : "+l"(row));
+    uint32_t *rowu = reinterpret_cast<uint32_t *>(row);
+    unsigned char *rowb = reinterpret_cast<unsigned char *>(row);
+#ifdef GF_TRACE
+    long long tr_t0 = 0, tr_t1 = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0));
+#endif
+    {  // init: row = -1 (geodesic_utils.py:113), visited = claimed = {} (:114)
+      const size_t head = ((16 - ((uintptr_t)row & 15)) & 15) / 4;
+      const size_t h = head < (size_t)N ? head : (size_t)N;
+      const size_t nvec = ((size_t)N - h) / 4;
+      float4 *r4 = reinterpret_cast<float4 *>(row + h);
+      const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
+      for (size_t i = tid; i < nvec; i += THREADS) r4[i] = m1;
+      if ((size_t)tid < h) row[tid] = -1.f;
+      const size_t tail0 = h + nvec * 4;
+      if ((size_t)tid < (size_t)N - tail0) row[tail0 + tid] = -1.f;
+      uint4 *b4 = reinterpret_cast<uint4 *>(vis);
+      for (int i = tid; i < words / 2; i += THREADS) b4[i] = make_uint4(0u, 0u, 0u, 0u);  // vis, clm contiguous
+    }
+    const int s = S.seeds[q];
+    const bool seed_ok = s >= 0 && s < N;  // the reference would raise an index error; the row stays -1
+    __syncthreads();
+    if (tid == 0) {
+      s_next_n[0] = s_next_n[1] = 0;
+      vis[(unsigned)N >> 5] |= 1u << (N & 31);  // the sentinel point N is "visited"
+      fq[0] = s;                                // frontier of level 1 = {seed}
+    }
+    __syncthreads();
+    int F = seed_ok ? 1 : 0;
+    // NOTE the seed is NOT marked visited before level 1: the reference's first expansion has no
+    // visited filter (:123), so a seed that appears in its own neighbour row is re-won at level 1.
+    int level = 0;
+    unsigned long long reached = 0;
+    float rmax = 0.f;  // largest distance this thread wrote into the row (all are >= 0)
+    // distance of a point won at level `won`: the key left in its row entry is the reference's winner.
+    // level 1: the distance is the edge itself (:127); later: edge + parent's distance (:139,:144)
+    auto resolve = [&](int t, int won) {
+      const uint32_t key = ld_cg_u32(rowu + t);
+      const unsigned p = (key & 0x7fffffffu) >> sb, j = key & (KP - 1);
+      const float w = __ldg(S.len + ((size_t)p << sb) + j);
+      const float d = won == 1 ? w : __fadd_rn(w, __uint_as_float(ld_cg_u32(rowu + p)));
+      row[t] = d;
+      rmax = fmaxf(rmax, d);
+    };
+#ifdef GF_TRACE
+#define GF_TR(slot)                                                                                              \
+  do {                                                                                                           \
+    if (a.trace2 && blockIdx.x < 4 && item < 4096 && level <= 40 && (tid & 31u) == 0 && tid < 1024)              \
+      a.trace2[((((size_t)blockIdx.x * 41 + level) * 32 + (tid >> 5)) * 8) + (slot)] = clock64();                 \
+  } while (0)
+#else
+#define GF_TR(slot) \
+  do {              \
+  } while (0)
+#endif
+    while (F > 0 && level < a.max_step) {
+      ++level;
+      GF_TR(0);
+      // first stage of this thread's own resolve: the key of its first frontier point (final since the barrier)
+      int rt = -1;
+      uint32_t rkey = 0;
+      if (level > 1 && (int)tid < F) {
+        rt = frontier((int)tid, (level - 1) & 1);
+        rkey = ld_cg_u32(rowu + rt);
+      }
+      // ---- claims: KP/4 lanes per frontier point; lanes past the end expand the sentinel point N -------------
+      const int Fs = F < QC ? F : QC;
+      for (int n0 = (int)group; n0 < Fs; n0 += (int)ngroups * U) {
+        unsigned pl[U];
+        int4 t[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int at = n0 + u * (int)ngroups;
+          pl[u] = (unsigned)(at < Fs ? fq_at(at) : N) << lsb;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = __ldg(trow + pl[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (u > 0 && n0 + u * (int)ngroups >= Fs) continue;  // whole groups of sentinel lanes
+          geo_claim4_enc(keybase | (pl[u] << 2), t[u], vis_s, clm_s, rowb);
+        }
+      }
+      for (int node = QC + (int)group; node < F; node += (int)ngroups) {  // spilled tail (rare)
+        const unsigned pl = (unsigned)ovf[ovf_at(node, (level - 1) & 1)] << lsb;
+        geo_claim4_enc(keybase | (pl << 2), __ldg(trow + pl), vis_s, clm_s, rowb);
+      }
+      GF_TR(1);
+      // ---- the frontier's own distances (its points were won at level-1 and still hold their keys) ----------
+      if (level > 1) {
+        float rw = 0.f, rpd = 0.f;
+        if (rt >= 0) {  // second stage: both loads in flight while the rest of the frontier is resolved
+          const unsigned p = (rkey & 0x7fffffffu) >> sb, j = rkey & (KP - 1);
+          rw = __ldg(S.len + ((size_t)p << sb) + j);
+          if (level > 2) rpd = __uint_as_float(ld_cg_u32(rowu + p));
+        }
+        for (int i = (int)tid + THREADS; i < F; i += THREADS) resolve(frontier(i, (level - 1) & 1), level - 1);
+        if (rt >= 0) {
+          const float d = level == 2 ? rw : __fadd_rn(rw, rpd);
+          row[rt] = d;
+          rmax = fmaxf(rmax, d);
+        }
+      }
+      GF_TR(2);
+      __syncthreads();
+      GF_TR(3);
+      // ---- commit: the points claimed at this level become visited (:140) and form the next frontier -------
+      if (tid == 0) s_next_n[(level + 1) & 1] = 0;  // idle since the previous level's reads; used after the next barrier
+      if (level == 1 && seed_ok && tid == (((unsigned)s >> 7) & (THREADS - 1))) {
+        // the seed joins the visited set now; if no self edge re-won it, its distance stays 0
+        // (a re-won seed holds its key until it is resolved with the other level-1 points)
+        if (ld_cg_u32(rowu + s) == GEO_UNVISITED) row[s] = 0.f;
+        vis[(unsigned)s >> 5] |= 1u << (s & 31);
+      }
+      {
+        uint4 *clm4 = reinterpret_cast<uint4 *>(clm), *vis4 = reinterpret_cast<uint4 *>(vis);
+        const int n4 = words >> 2;  // a multiple of 4 words
+        int *cnt = &s_next_n[level & 1];
+        const int par = level & 1;
+        for (int i = tid; i < n4; i += THREADS) {
+          const uint4 c = clm4[i];
+          if ((c.x | c.y | c.z | c.w) == 0u) continue;
+          clm4[i] = make_uint4(0u, 0u, 0u, 0u);
+          uint4 v = vis4[i];
+          v.x |= c.x, v.y |= c.y, v.z |= c.z, v.w |= c.w;
+          vis4[i] = v;
+          const int n = __popc(c.x) + __popc(c.y) + __popc(c.z) + __popc(c.w);
+          int at = atomicAdd(cnt, n);
+          const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+          if (at + n <= QC) {  // the usual case: the whole piece lands in the on-chip queue
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              for (uint32_t m = cw[k4]; m; m &= m - 1) fq[at++] = i * 128 + k4 * 32 + __ffs((int)m) - 1;
+          } else {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              for (uint32_t m = cw[k4]; m; m &= m - 1) {
+                const int t = i * 128 + k4 * 32 + __ffs((int)m) - 1;
+                if (at < QC)
+                  fq[at] = t;
+                else
+                  ovf[ovf_at(at, par)] = t;
+                ++at;
+              }
+          }
+        }
+      }
+      GF_TR(4);
+      __syncthreads();
+      GF_TR(5);
+      const int nextF = s_next_n[level & 1];
+#ifdef GF_TRACE
+      if (a.trace2 && blockIdx.x < 4 && item < 4096 && level <= 40 && tid == 0)
+        a.trace2[((((size_t)blockIdx.x * 41 + level) * 32) * 8) + 6] = F, a.trace2[((((size_t)blockIdx.x * 41 + level) * 32) * 8) + 7] = nextF;
+#endif
+      reached += (unsigned long long)nextF;
+      F = nextF;
+    }
+    // the points won at the last executed level still hold their keys
+    if (level >= 1)
+      for (int i = tid; i < F; i += THREADS) resolve(frontier(i, level & 1), level);
+    if (level == 0 && seed_ok && tid == 0) row[s] = 0.f;  // max_step <= 0: only the seed entry (:118)
+    if (S.row_max) {
+      // max over the row = max over what was written (the seed's 0 included), or -1 for a row that stayed empty;
+      // distances are non-negative, so their bit patterns order like unsigned integers
+      const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(rmax));
+      if ((tid & 31u) == 0) s_rmax[tid >> 5] = wm;
+      __syncthreads();
+      if (tid < 32) {
+        const uint32_t v = tid < THREADS / 32 ? s_rmax[tid] : 0u;
+        const uint32_t m = __reduce_max_sync(0xffffffffu, v);
+        if (tid == 0) S.row_max[q] = seed_ok ? __uint_as_float(m) : -1.f;
+      }
+    }
+    if (tid == 0 && S.stats) {
+      if (reached) atomicAdd(S.stats, reached);
+      // the deepest level that won anything: the last level's frontier is empty exactly when the loop ended on F == 0
+      const int deepest = (level > 0 && F == 0) ? level - 1 : level;
+      atomicMax(S.stats + 1, (unsigned long long)(reached ? deepest : 0));
+    }
+#ifdef GF_TRACE
+    __syncthreads();
+    if (tid == 0 && item < 1024 && a.trace) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t1));
+      a.trace[item * 4 + 0] = tr_t0, a.trace[item * 4 + 1] = tr_t1;
+      a.trace[item * 4 + 2] = (long long)reached, a.trace[item * 4 + 3] = ((long long)blockIdx.x << 32) | level;
+    }
+#endif
   }
 }
 
@@ -429,6 +726,15 @@ static int geo_slot_bits(int k) {
   return sb < 2 ? 2 : sb;
 }
 
+// ---- planning ---------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static int geo_bitmap_words(int N) { return ((N + 1 + 127) / 128) * 4; }  // + the sentinel point N; whole 16-byte pieces
+
+// plan of the template kernel (big scenes, seed-sharded scenes, or GF_GEO_ENC=0)
 struct GeoPlan {
   int grid, bitmap_words, mode, threads;
   size_t smem;
@@ -436,16 +742,10 @@ struct GeoPlan {
 
 // shared-memory plan, identical for sizing and launching: 227 KB usable per SM on sm_100 (1 KB reserved per CTA)
 static void geo_smem_plan(int N, GeoPlan *p, int *ctas_per_sm) {
-  const int words = ((N + 1 + 127) / 128) * 4;  // + the sentinel point N; whole 16-byte pieces
-  static int max_mode = -1, force_threads = 0;
-  if (max_mode < 0) {
-    const char *e = getenv("GF_GEO_NOBITMAP");  // test knob: 1 = no on-chip state, 2 = visited bitmap only
-    const int v = e ? atoi(e) : 0;
-    const char *t = getenv("GF_GEO_THREADS");  // experiment knob: 512 or 1024
-    force_threads = t ? atoi(t) : 0;
-    max_mode = v == 1 ? 0 : (v == 2 ? 1 : 2);
-  }
-  int m = max_mode;
+  const int words = geo_bitmap_words(N);
+  static const int nobitmap = env_int("GF_GEO_NOBITMAP", 0);  // test knob: 1 = no on-chip state, 2 = visited bitmap only
+  static const int force_threads = env_int("GF_GEO_THREADS", 0);
+  int m = nobitmap == 1 ? 0 : (nobitmap == 2 ? 1 : 2);
   auto bytes_of = [&](int mode) {
     return sizeof(int) * (size_t)(mode == 2 ? 1 : 2) * GEO_QCAP + sizeof(uint32_t) * (size_t)mode * words;
   };
@@ -456,10 +756,7 @@ static void geo_smem_plan(int N, GeoPlan *p, int *ctas_per_sm) {
   const size_t bytes = bytes_of(m);
   int fit = (int)((size_t)(227 * 1024) / (bytes + 1024));
   if (fit < 1) fit = 1;
-  // 1024-thread CTAs, two per SM.  (Four 512-thread CTAs per SM were measured at c2: +3 % throughput with
-  // four scenes in flight, -8 % for a scene alone, -25 % at c4 -- kept behind GF_GEO_THREADS=512.)
-  int threads = 1024;
-  if (force_threads == 512 || force_threads == 1024) threads = force_threads;
+  const int threads = force_threads == 512 ? 512 : 1024;
   const int cap = 2048 / threads;
   p->bitmap_words = m > 0 ? words : 0;
   p->smem = bytes;
@@ -468,37 +765,255 @@ static void geo_smem_plan(int N, GeoPlan *p, int *ctas_per_sm) {
   *ctas_per_sm = fit < cap ? fit : cap;
 }
 
-static int plan_geo(int N, int Q, GeoPlan *p) {
+static void plan_geo(int N, int Q, GeoPlan *p) {
   int per_sm = 1;
   geo_smem_plan(N, p, &per_sm);
-  static int bps_cap = -1;
-  if (bps_cap < 0) {
-    const char *e = getenv("GF_GEO_BPS");  // experiment knob
-    bps_cap = e ? atoi(e) : 0;
-  }
+  static const int bps_cap = env_int("GF_GEO_BPS", 0);  // experiment knob
   if (bps_cap > 0 && per_sm > bps_cap) per_sm = bps_cap;
   int grid = num_sms() * per_sm;
   if (grid > Q) grid = Q;
   p->grid = grid < 1 ? 1 : grid;
-  return GF_OK;
+}
+
+// plan of the batched kernel
+struct GeoBatchPlan {
+  int threads, unroll, per_sm, grid, qcap, words;
+  size_t smem, ovf_stride;
+};
+constexpr size_t GEO_OVF_BUDGET = (size_t)192 << 20;  // bytes of frontier overflow a launch may reserve
+
+// true when the scene can run in the batched kernel (both bitmaps + a queue fit one CTA's shared memory)
+static bool geo_batchable(int maxN) {
+  static const int nobitmap = env_int("GF_GEO_NOBITMAP", 0), enc = env_int("GF_GEO_ENC", 2);
+  if (nobitmap != 0 || enc == 0) return false;
+  return sizeof(int) * 1024 + 2 * sizeof(uint32_t) * (size_t)geo_bitmap_words(maxN) <= (size_t)226 * 1024;
+}
+
+static void plan_batch(int maxN, long long items, GeoBatchPlan *p) {
+  static const int force_threads = env_int("GF_GEO_THREADS", 0), unroll = env_int("GF_GEO_UNROLL", 2),
+                   bps_cap = env_int("GF_GEO_BPS", 0), many_threads = env_int("GF_GEO_BATCH_THREADS", 512);
+  const int sms = num_sms();
+  p->words = geo_bitmap_words(maxN);
+  // One scene's worth of seeds cannot fill the thread slots anyway and a launch lasts as long as its slowest
+  // seed: 1024 threads per seed.  A batch is throughput work: more, smaller CTAs per SM (see the kernel's header).
+  int threads = items <= 2ll * sms ? 1024 : many_threads;
+  if (force_threads == 256 || force_threads == 512 || force_threads == 1024) threads = force_threads;
+  if (threads != 256 && threads != 512 && threads != 1024) threads = 512;
+  const int cap = 2048 / threads;
+  int best_fit = 0, best_q = 0;
+  for (int qcap = 4096; qcap >= 1024 && qcap >= threads; qcap >>= 1) {
+    const size_t bytes = sizeof(int) * (size_t)qcap + 2 * sizeof(uint32_t) * (size_t)p->words;
+    if (bytes > (size_t)226 * 1024) continue;
+    int fit = (int)((size_t)(227 * 1024) / (bytes + 1024));
+    if (fit > cap) fit = cap;
+    if (fit > best_fit) best_fit = fit, best_q = qcap;  // the largest queue that reaches the most CTAs per SM
+  }
+  if (best_fit < 1) best_fit = 1, best_q = 1024;
+  if (bps_cap > 0 && best_fit > bps_cap) best_fit = bps_cap;
+  p->threads = threads;
+  p->unroll = unroll == 1 ? 1 : 2;
+  p->per_sm = best_fit;
+  p->qcap = best_q;
+  p->smem = sizeof(int) * (size_t)best_q + 2 * sizeof(uint32_t) * (size_t)p->words;
+  p->ovf_stride = (size_t)maxN + 2;
+  long long grid = (long long)sms * best_fit;
+  const long long ovf_cap = (long long)(GEO_OVF_BUDGET / (sizeof(int) * p->ovf_stride));
+  if (grid > ovf_cap) grid = ovf_cap > sms ? ovf_cap : sms;
+  if (grid > items) grid = items;
+  p->grid = (int)(grid < 1 ? 1 : grid);
+}
+
+static size_t geo_edge_bytes(int N, int k) {
+  return 2 * align256(sizeof(int) * (((size_t)N + 1) << geo_slot_bits(k)));
+}
+
+// scratch of one batched launch: frontier overflow + the item counter
+size_t geodesic_batch_scratch_bytes(int maxN, long long items) {
+  GeoBatchPlan p;
+  plan_batch(maxN, items, &p);
+  return align256(sizeof(int) * p.ovf_stride * (size_t)p.grid) + align256(256) + 512;
 }
 
 size_t geodesic_workspace_bytes(int N, int k, int Q) {
-  int per_sm = 1;
+  size_t b = geo_edge_bytes(N, k);  // packed edge targets + lengths (+ sentinel row)
+  if (geo_batchable(N)) return b + geodesic_batch_scratch_bytes(N, Q) + 1024;
   GeoPlan pl;
-  geo_smem_plan(N, &pl, &per_sm);
-  long long grid = (long long)num_sms() * per_sm;
-  if (grid > Q) grid = Q;
-  if (grid < 1) grid = 1;
-  const int sb = geo_slot_bits(k);
-  size_t b = 0;
-  b += align256(sizeof(int) * (((size_t)N + 1) << sb)) * 2;     // packed edge targets + lengths (+ sentinel row)
-  b += align256(sizeof(int) * ((size_t)N + 2) * (size_t)grid);  // frontier overflow
-  b += align256(64);                                             // seed counter
-  b += align256(64);                                             // stats
+  plan_geo(N, Q, &pl);
+  b += align256(sizeof(int) * ((size_t)N + 2) * (size_t)pl.grid);  // frontier overflow
+  b += align256(256);                                              // seed counter + stats
   return b + 1024;
 }
 
+// workspace carve-up of the single-scene entry points, identical for sizing, packing and launching
+struct GeoBuffers {
+  int *tgt;
+  float *len;
+  void *rest;  // overflow + control block (layout depends on the kernel)
+  size_t rest_bytes;
+};
+static bool geo_carve(void *workspace, size_t workspace_bytes, int N, int slot_bits, GeoBuffers *b) {
+  Arena a(workspace, workspace_bytes);
+  b->tgt = a.take<int>(((size_t)N + 1) << slot_bits);
+  b->len = a.take<float>(((size_t)N + 1) << slot_bits);
+  b->rest = a.ok ? (void *)(a.base + a.off) : nullptr;
+  b->rest_bytes = a.ok ? a.size - a.off : 0;
+  return a.ok;
+}
+
+int geodesic_edge_buffers(void *workspace, size_t workspace_bytes, int N, int k, int Q, int **tgt, float **len,
+                          int *slot_bits, int *enc) {
+  (void)Q;
+  GeoBuffers b;
+  *slot_bits = geo_slot_bits(k);
+  if (!geo_carve(workspace, workspace_bytes, N, *slot_bits, &b)) {
+    set_error("geodesic: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              geodesic_workspace_bytes(N, k, Q));
+    return GF_ERR_WORKSPACE;
+  }
+  *tgt = b.tgt, *len = b.len;
+  *enc = geo_batchable(N) ? 1 : 0;
+  return GF_OK;
+}
+int geodesic_edge_format(int N) { return geo_batchable(N) ? 1 : 0; }
+
+// the opt-in to more than 48 KB of dynamic shared memory is a per-function, per-device attribute: set it once
+// to the most any plan can ask for instead of before every launch (several host threads launch concurrently)
+template <typename K>
+static int geo_kernel_ready(K kernel, int *done) {
+  int dev = 0;
+  GF_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!__atomic_load_n(&done[dev], __ATOMIC_ACQUIRE)) {
+    GF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    __atomic_store_n(&done[dev], 1, __ATOMIC_RELEASE);
+  }
+  return GF_OK;
+}
+
+#ifdef GF_TRACE
+static long long *g_trace = nullptr, *g_trace2 = nullptr;
+static const size_t kTrace2N = (size_t)4 * 41 * 32 * 8;
+static void trace_dump(int items, cudaStream_t st) {
+  static int calls = 0;
+  if (++calls != 3) return;
+  static long long h[4 * 1024];
+  cudaStreamSynchronize(st);
+  cudaMemcpy(h, g_trace, sizeof(h), cudaMemcpyDeviceToHost);
+  long long t0 = h[0];
+  for (int q = 0; q < items && q < 1024; ++q) t0 = h[q * 4] < t0 ? h[q * 4] : t0;
+  for (int q = 0; q < items && q < 1024; ++q)
+    fprintf(stderr, "TRACE seed %4d cta %3lld start_us=%8.2f dur_us=%8.2f reached=%7lld levels=%3lld\n", q,
+            h[q * 4 + 3] >> 32, (h[q * 4] - t0) * 1e-3, (h[q * 4 + 1] - h[q * 4]) * 1e-3, h[q * 4 + 2],
+            h[q * 4 + 3] & 0xffffffffll);
+  // per level of CTAs 0..3 (their first seed): phase boundaries in cycles relative to the level's start, as
+  // the minimum / maximum over the warps: claims done | resolve done | past barrier 1 | commit done | past barrier 2
+  static long long h2[4 * 41 * 32 * 8];
+  cudaMemcpy(h2, g_trace2, sizeof(h2), cudaMemcpyDeviceToHost);
+  for (int c = 0; c < 4; ++c)
+    for (int lv = 1; lv <= 40; ++lv) {
+      const long long *b = h2 + (((size_t)c * 41 + lv) * 32) * 8;
+      if (!b[0]) continue;
+      long long t00 = b[0];
+      for (int w = 0; w < 32; ++w)
+        if (b[w * 8] && b[w * 8] < t00) t00 = b[w * 8];
+      fprintf(stderr, "TRACE2 cta %d level %2d F=%5lld next=%5lld |", c, lv, b[6], b[7]);
+      for (int sl = 0; sl < 6; ++sl) {
+        long long mn = 1ll << 60, mx = 0;
+        for (int w = 0; w < 32; ++w) {
+          const long long v = b[w * 8 + sl] - t00;
+          if (b[w * 8 + sl] == 0 || (sl >= 6)) continue;
+          mn = v < mn ? v : mn, mx = v > mx ? v : mx;
+        }
+        fprintf(stderr, " %6lld..%-6lld", mn, mx);
+      }
+      fprintf(stderr, "\n");
+    }
+}
+#endif
+
+// One launch over the (scene, seed) items of up to GEO_MAXB scenes whose edge tables are already packed
+// (encoded targets).  scratch: geodesic_batch_scratch_bytes(max N, total seeds).
+int geodesic_batch_launch(const GeoSceneDesc *scenes, int B, int k, int max_step, void *scratch, size_t scratch_bytes,
+                          cudaStream_t st) {
+  if (B < 1 || B > GEO_MAXB) {
+    set_error("geodesic: %d scenes in a batched launch, 1..%d supported", B, GEO_MAXB);
+    return GF_ERR_INVALID;
+  }
+  GeoBatchArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  int maxN = 0;
+  long long items = 0;
+  const int slot_bits = geo_slot_bits(k);
+  for (int b = 0; b < B; ++b) {
+    const GeoSceneDesc &d = scenes[b];
+    if ((((unsigned long long)d.N + 1) << slot_bits) >= GEO_KEYMAX) {
+      set_error("geodesic: N=%d with k=%d does not fit the 30-bit claim key (N << %d must be < 2^30)", d.N, k,
+                slot_bits);
+      return GF_ERR_INVALID;
+    }
+    GeoScene &s = ga.sc[b];
+    s.tgt = d.tgt, s.len = d.len, s.seeds = d.seeds, s.geo = d.geo, s.row_max = d.row_max;
+    s.stats = (unsigned long long *)d.stats;
+    s.N = d.N, s.Q = d.Q, s.item0 = (int)items, s.bitmap_words = geo_bitmap_words(d.N);
+    items += d.Q;
+    maxN = d.N > maxN ? d.N : maxN;
+  }
+  if (items == 0) return GF_OK;
+  if (!geo_batchable(maxN) || items > 0x7fffffffll) {
+    set_error("geodesic: a scene of %d points does not fit the batched kernel", maxN);
+    return GF_ERR_INVALID;
+  }
+  GeoBatchPlan p;
+  plan_batch(maxN, items, &p);
+  Arena a(scratch, scratch_bytes);
+  ga.overflow = a.take<int>(p.ovf_stride * (size_t)p.grid);
+  ga.item_counter = a.take<unsigned>(64);
+  if (!a.ok) {
+    set_error("geodesic: scratch too small (%zu bytes given, %zu needed)", scratch_bytes,
+              geodesic_batch_scratch_bytes(maxN, items));
+    return GF_ERR_WORKSPACE;
+  }
+  ga.ovf_stride = p.ovf_stride;
+  ga.B = B, ga.total_items = (int)items, ga.max_step = max_step, ga.slot_bits = slot_bits, ga.qcap = p.qcap;
+  GF_CUDA(cudaMemsetAsync(ga.item_counter, 0, 256, st));
+#ifdef GF_TRACE
+  if (!g_trace) cudaMalloc(&g_trace, 8 * 4 * 1024), cudaMalloc(&g_trace2, kTrace2N * 8);
+  cudaMemsetAsync(g_trace, 0, 8 * 4 * 1024, st);
+  cudaMemsetAsync(g_trace2, 0, kTrace2N * 8, st);
+  ga.trace = g_trace, ga.trace2 = g_trace2;
+#endif
+  stage_mark(ST_GEO_READY, st);
+  int rc = GF_OK;
+#define GF_GEO_BATCH(T, U)                                            \
+  do {                                                                \
+    static int done[64] = {0};                                        \
+    rc = geo_kernel_ready(geo_bfs_batch_kernel<T, U>, done);          \
+    if (rc) return rc;                                                \
+    geo_bfs_batch_kernel<T, U><<<p.grid, T, p.smem, st>>>(ga);        \
+  } while (0)
+  if (p.threads == 256 && p.unroll == 1)
+    GF_GEO_BATCH(256, 1);
+  else if (p.threads == 256)
+    GF_GEO_BATCH(256, 2);
+  else if (p.threads == 512 && p.unroll == 1)
+    GF_GEO_BATCH(512, 1);
+  else if (p.threads == 512)
+    GF_GEO_BATCH(512, 2);
+  else if (p.unroll == 1)
+    GF_GEO_BATCH(1024, 1);
+  else
+    GF_GEO_BATCH(1024, 2);
+#undef GF_GEO_BATCH
+  GF_LAUNCHED();
+#ifdef GF_TRACE
+  trace_dump((int)items, st);
+#endif
+  stage_mark(ST_GEO_DONE, st);
+  return GF_OK;
+}
+
+// One scene.  D == nullptr: the edge table in the workspace has already been written (by the kNN query kernel of
+// the fused hot path, gf_knn.cu TopK::store_edges, in the format geodesic_edge_buffers reported) -- no packing pass.
 int geodesic_run(const float *D, const void *I, int is64, int N, int k, const int *seeds, int Q, float radius,
                  int max_step, float *geo, int64_t *stats_out, void *workspace, size_t workspace_bytes,
                  cudaStream_t st, float *const *peer_rows, int n_peers, float *row_max) {
@@ -506,41 +1021,66 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
     set_error("geodesic: %d peers given, at most %d supported", n_peers, GEO_MAX_PEERS);
     return GF_ERR_INVALID;
   }
-  GeoPlan p;
-  int rc = plan_geo(N, Q, &p);
-  if (rc) return rc;
   const int slot_bits = geo_slot_bits(k);
   if ((((unsigned long long)N + 1) << slot_bits) >= GEO_KEYMAX) {
     set_error("geodesic: N=%d with k=%d does not fit the 30-bit claim key (N << %d must be < 2^30)", N, k, slot_bits);
     return GF_ERR_INVALID;
   }
-  Arena a(workspace, workspace_bytes);
-  int *tgt = a.take<int>(((size_t)N + 1) << slot_bits);
-  float *len = a.take<float>(((size_t)N + 1) << slot_bits);
-  int *overflow = a.take<int>(((size_t)N + 2) * (size_t)p.grid);
-  unsigned *counter = a.take<unsigned>(16);
-  unsigned long long *stats = a.take<unsigned long long>(8);
-  if (!a.ok) {
+  GeoBuffers b;
+  if (!geo_carve(workspace, workspace_bytes, N, slot_bits, &b) ||
+      workspace_bytes < geodesic_workspace_bytes(N, k, Q) - 1024) {
     set_error("geodesic: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
               geodesic_workspace_bytes(N, k, Q));
     return GF_ERR_WORKSPACE;
   }
-  GF_CUDA(cudaMemsetAsync(counter, 0, 64, st));
-  GF_CUDA(cudaMemsetAsync(stats, 0, 64, st));
-  {
+  const bool batched = geo_batchable(N);  // also the format of an already packed edge table
+  if (D != nullptr) {
     const long long total = ((long long)N + 1) << slot_bits;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     const int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
     if (is64)
-      geo_pack_edges_kernel<true><<<grid, 256, 0, st>>>(D, I, N, k, radius, slot_bits, tgt, len);
+      geo_pack_edges_kernel<true><<<grid, 256, 0, st>>>(D, I, N, k, radius, slot_bits, batched ? 1 : 0, b.tgt, b.len);
     else
-      geo_pack_edges_kernel<false><<<grid, 256, 0, st>>>(D, I, N, k, radius, slot_bits, tgt, len);
+      geo_pack_edges_kernel<false><<<grid, 256, 0, st>>>(D, I, N, k, radius, slot_bits, batched ? 1 : 0, b.tgt, b.len);
     GF_LAUNCHED();
   }
+  if (batched && n_peers == 0) {
+    // stats of the batched kernel are accumulated with atomics: clear them here (16 bytes of the control block)
+    Arena a(b.rest, b.rest_bytes);
+    GeoBatchPlan p;
+    plan_batch(N, Q, &p);
+    (void)a.take<int>(p.ovf_stride * (size_t)p.grid);
+    unsigned *ctl = a.take<unsigned>(64);
+    unsigned long long *stats = (unsigned long long *)(ctl + 32);  // second half of the 256-byte control block
+    GeoSceneDesc d;
+    d.tgt = b.tgt, d.len = b.len, d.seeds = seeds, d.geo = geo, d.row_max = row_max;
+    d.stats = stats_out ? (int64_t *)stats : nullptr;
+    d.N = N, d.Q = Q;
+    int rc = geodesic_batch_launch(&d, 1, k, max_step, b.rest, b.rest_bytes, st);  // its memset clears the stats too
+    if (rc) return rc;
+    if (stats_out) GF_CUDA(cudaMemcpyAsync(stats_out, stats, 16, cudaMemcpyDeviceToDevice, st));
+    return GF_OK;
+  }
+  if (batched) {
+    set_error("geodesic: seed-sharded scenes use the plain edge format (internal error)");
+    return GF_ERR_INVALID;
+  }
+  GeoPlan p;
+  plan_geo(N, Q, &p);
+  Arena a(b.rest, b.rest_bytes);
+  int *overflow = a.take<int>(((size_t)N + 2) * (size_t)p.grid);
+  unsigned *counter = a.take<unsigned>(64);
+  unsigned long long *stats = (unsigned long long *)(counter + 32);
+  if (!a.ok) {
+    set_error("geodesic: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              geodesic_workspace_bytes(N, k, Q));
+    return GF_ERR_WORKSPACE;
+  }
+  GF_CUDA(cudaMemsetAsync(counter, 0, 256, st));  // seed counter + stats
   stage_mark(ST_GEO_READY, st);
   GeoArgs ga;
-  ga.tgt = tgt, ga.len = len, ga.N = N, ga.Q = Q, ga.max_step = max_step, ga.slot_bits = slot_bits;
+  ga.tgt = b.tgt, ga.len = b.len, ga.N = N, ga.Q = Q, ga.max_step = max_step, ga.slot_bits = slot_bits;
   ga.seeds = seeds, ga.geo = geo, ga.overflow = overflow, ga.seed_counter = counter, ga.stats = stats;
   ga.bitmap_words = p.bitmap_words;
   ga.row_max = row_max;
@@ -552,16 +1092,15 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
       return GF_ERR_INVALID;
     }
 #ifdef GF_TRACE
-  static long long *d_trace = nullptr;
-  if (!d_trace) cudaMalloc(&d_trace, 8 * 4 * 1024);
-  cudaMemsetAsync(d_trace, 0, 8 * 4 * 1024, st);
-  ga.trace = d_trace;
+  ga.trace = nullptr, ga.trace2 = nullptr;
 #endif
-#define GF_GEO_LAUNCH(M, T)                                                                                   \
-  do {                                                                                                        \
-    GF_CUDA(cudaFuncSetAttribute(geo_seed_bfs_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                 (int)p.smem));                                                               \
-    geo_seed_bfs_kernel<M, T><<<p.grid, T, p.smem, st>>>(ga);                                                 \
+  int rc = GF_OK;
+#define GF_GEO_LAUNCH(M, T)                                        \
+  do {                                                             \
+    static int done[64] = {0};                                     \
+    rc = geo_kernel_ready(geo_seed_bfs_kernel<M, T>, done);        \
+    if (rc) return rc;                                             \
+    geo_seed_bfs_kernel<M, T><<<p.grid, T, p.smem, st>>>(ga);      \
   } while (0)
   if (p.mode == 2 && p.threads == 512)
     GF_GEO_LAUNCH(2, 512);
@@ -577,22 +1116,6 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
     GF_GEO_LAUNCH(0, 1024);
 #undef GF_GEO_LAUNCH
   GF_LAUNCHED();
-#ifdef GF_TRACE
-  {
-    static int calls = 0;
-    if (++calls == 3) {
-      static long long h[4 * 1024];
-      cudaStreamSynchronize(st);
-      cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
-      long long t0 = h[0];
-      for (int q = 0; q < Q && q < 1024; ++q) t0 = h[q * 4] < t0 ? h[q * 4] : t0;
-      for (int q = 0; q < Q && q < 1024; ++q)
-        fprintf(stderr, "TRACE seed %4d cta %3lld start_us=%8.2f dur_us=%8.2f reached=%7lld levels=%3lld\n", q,
-                h[q * 4 + 3] >> 32, (h[q * 4] - t0) * 1e-3, (h[q * 4 + 1] - h[q * 4]) * 1e-3, h[q * 4 + 2],
-                h[q * 4 + 3] & 0xffffffffll);
-    }
-  }
-#endif
   stage_mark(ST_GEO_DONE, st);
   if (stats_out) GF_CUDA(cudaMemcpyAsync(stats_out, stats, 16, cudaMemcpyDeviceToDevice, st));
   return GF_OK;

@@ -10,15 +10,19 @@
 
 namespace gf {
 
+// Auxiliary streams of the fused path, one set per (device, caller stream) of the calling thread: FPS (a <= 16-SM
+// cluster, latency bound) runs next to the kNN kernels, and the scenes of a batch run side by side on LANES
+// lanes.  Callers that keep several calls in flight on several streams get one set per stream, so their kernels
+// do not queue on a single hidden stream.  FPS lanes have the highest priority: FPS is the longest dependency
+// chain of a scene, its cluster should be placed as soon as SMs free up.
+constexpr int LANES = 4;
 struct ForkJoin {
-  cudaStream_t aux = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t fps[LANES] = {}, knn[LANES] = {};  // knn[0] stays null: lane 0 builds its graph on the caller's stream
+  cudaEvent_t fork = nullptr, join_fps[LANES] = {}, join_knn[LANES] = {};
+  cudaStream_t aux = nullptr;  // = fps[0] (single-scene entry points)
+  cudaEvent_t join = nullptr;  // = join_fps[0]
 };
 
-// One auxiliary stream per (device, caller stream) of the calling thread, so that callers that keep several
-// scenes in flight on several streams also get their FPS kernels (one 16-SM cluster each, latency bound)
-// running side by side instead of queueing on a single hidden stream.  Highest priority: FPS is the longest
-// dependency chain of a step, its cluster should be placed as soon as SMs free up.
 static int get_fork_join(cudaStream_t user, ForkJoin **out) {
   constexpr int SLOTS = 16;
   struct Entry {
@@ -45,9 +49,16 @@ static int get_fork_join(cudaStream_t user, ForkJoin **out) {
     if (e && !e->used) {
       int lo = 0, hi = 0;
       GF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = greatest priority
-      GF_CUDA(cudaStreamCreateWithPriority(&e->fj.aux, cudaStreamNonBlocking, hi));
-      GF_CUDA(cudaEventCreateWithFlags(&e->fj.fork, cudaEventDisableTiming));
-      GF_CUDA(cudaEventCreateWithFlags(&e->fj.join, cudaEventDisableTiming));
+      ForkJoin &f = e->fj;
+      GF_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
+      for (int l = 0; l < LANES; ++l) {
+        GF_CUDA(cudaStreamCreateWithPriority(&f.fps[l], cudaStreamNonBlocking, hi));
+        GF_CUDA(cudaEventCreateWithFlags(&f.join_fps[l], cudaEventDisableTiming));
+        if (l > 0) GF_CUDA(cudaStreamCreateWithPriority(&f.knn[l], cudaStreamNonBlocking, lo));
+        GF_CUDA(cudaEventCreateWithFlags(&f.join_knn[l], cudaEventDisableTiming));
+      }
+      f.aux = f.fps[0];
+      f.join = f.join_fps[0];
       e->used = true;
       e->dev = dev;
     }
@@ -62,7 +73,7 @@ static int get_fork_join(cudaStream_t user, ForkJoin **out) {
 }
 
 struct GuidancePlan {
-  size_t fps, knn, geo, dist, idx, total;
+  size_t fps, knn, geo, total;
 };
 
 static GuidancePlan plan_guidance(int N, int Q, int k) {
@@ -70,9 +81,7 @@ static GuidancePlan plan_guidance(int N, int Q, int k) {
   p.fps = align256(gf_fps_workspace_bytes(1, N, Q));
   p.knn = align256(knn_grid_workspace_bytes(N));
   p.geo = align256(geodesic_workspace_bytes(N, k, Q));
-  p.dist = align256(sizeof(float) * (size_t)N * k);
-  p.idx = align256(sizeof(int) * (size_t)N * k);
-  p.total = p.fps + p.knn + p.geo + p.dist + p.idx + 1024;
+  p.total = p.fps + p.knn + p.geo + 1024;
   return p;
 }
 
@@ -105,10 +114,6 @@ static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, in
   void *ws_knn = w;
   w += p.knn;
   void *ws_geo = w;
-  w += p.geo;
-  float *dist = knn_dist ? knn_dist : (float *)w;
-  w += p.dist;
-  int *idx = knn_idx32 ? knn_idx32 : (int *)w;
 
   ForkJoin *fj = nullptr;
   int rc = GF_OK;
@@ -128,13 +133,19 @@ static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, in
   rc = knn_grid_build(xyz, N, k, ws_knn, p.knn, st, &gb);
   if (rc) return rc;
   stage_mark(ST_KNN_BUILT, st);
-  rc = knn_grid_query(gb, nullptr, N, k, /*sqrt=*/1, dist, nullptr, idx, st);
+  // the query kernel writes the propagation's edge table straight from its registers; the (N,k) distance / index
+  // arrays are only written when the caller asked for them
+  KnnEdgeOut eo;
+  eo.radius = radius;
+  rc = geodesic_edge_buffers(ws_geo, p.geo, N, k, Q, &eo.tgt, &eo.len, &eo.slot_bits, &eo.enc);
+  if (rc) return rc;
+  rc = knn_grid_query(gb, nullptr, N, k, /*sqrt=*/1, knn_dist, nullptr, knn_idx32, st, &eo);
   if (rc) return rc;
   // join, then propagate
   if (!seeds_given) GF_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   stage_mark(ST_KNN_DONE, st);
-  return geodesic_run(dist, idx, /*is64=*/0, N, k, seeds, Q, radius, max_step, geo, stats, ws_geo, p.geo, st, peer_geo,
-                      n_peers, row_max);
+  return geodesic_run(nullptr, nullptr, /*is64=*/0, N, k, seeds, Q, radius, max_step, geo, stats, ws_geo, p.geo, st,
+                      peer_geo, n_peers, row_max);
 }
 
 extern "C" int gf_guidance(const float *xyz, int N, int Q, int k, float radius, int max_step, int *seeds, float *geo,
@@ -156,6 +167,125 @@ extern "C" int gf_guidance_seeded_scatter(const float *xyz, int N, const int *se
                                           int64_t *stats, void *workspace, size_t workspace_bytes, void *stream) {
   return guidance_impl(xyz, N, Q, k, radius, max_step, const_cast<int *>(seeds), 1, geo, nullptr, nullptr, stats,
                        workspace, workspace_bytes, stream, peer_geo, n_peers);
+}
+
+// ---- a batch of scenes (the reference's call is batched: geodesic_utils.py:98 loops over the scenes) -------------
+namespace gf {
+struct BatchPlan {
+  size_t per_scene[GEO_BATCH_MAX * 4];  // offsets of (fps, knn, edges) per scene
+  size_t scratch, scratch_bytes, stats, total;
+};
+static int plan_batch_guidance(const int *Ns, int B, int Q, int k, BatchPlan *p, size_t *fps_b, size_t *knn_b,
+                               size_t *edge_b) {
+  size_t off = 0;
+  int maxN = 1;
+  for (int b = 0; b < B; ++b) {
+    const int N = Ns[b];
+    fps_b[b] = align256(gf_fps_workspace_bytes(1, N, Q));
+    knn_b[b] = align256(knn_grid_workspace_bytes(N));
+    // the edge tables are the head of a single-scene geodesic workspace; only that head is used here
+    edge_b[b] = align256(geodesic_workspace_bytes(N, k, 1));
+    p->per_scene[b * 3 + 0] = off, off += fps_b[b];
+    p->per_scene[b * 3 + 1] = off, off += knn_b[b];
+    p->per_scene[b * 3 + 2] = off, off += edge_b[b];
+    maxN = N > maxN ? N : maxN;
+  }
+  p->scratch = off;
+  p->scratch_bytes = align256(geodesic_batch_scratch_bytes(maxN, (long long)Q * B));
+  off += p->scratch_bytes;
+  p->stats = off;
+  off += align256(16 * (size_t)B);
+  p->total = off + 1024;
+  return maxN;
+}
+}  // namespace gf
+
+extern "C" size_t gf_guidance_batch_workspace_bytes(const int *Ns, int B, int Q, int k) {
+  if (!Ns || B <= 0 || B > GEO_BATCH_MAX || Q <= 0 || k <= 0) return 0;
+  for (int b = 0; b < B; ++b)
+    if (Ns[b] <= 0) return 0;
+  BatchPlan p;
+  size_t f[GEO_BATCH_MAX], n[GEO_BATCH_MAX], e[GEO_BATCH_MAX];
+  plan_batch_guidance(Ns, B, Q, k, &p, f, n, e);
+  return p.total;
+}
+
+extern "C" int gf_guidance_batch(const float *const *xyz, const int *Ns, int B, int Q, int k, float radius,
+                                 int max_step, int *const *seeds, int seeds_given, float *const *geo,
+                                 float *const *row_max, int64_t *stats, void *workspace, size_t workspace_bytes,
+                                 void *stream) {
+  GF_CHECK_ARG(xyz && Ns && seeds && geo, "guidance_batch: null pointer array");
+  GF_CHECK_ARG(B >= 1 && B <= GEO_BATCH_MAX, "guidance_batch: B=%d outside [1,%d]", B, GEO_BATCH_MAX);
+  GF_CHECK_ARG(Q >= 1, "guidance_batch: need Q >= 1");
+  GF_CHECK_ARG(k >= 1 && k <= KNN_MAX_K, "guidance_batch: k=%d outside [1,%d]", k, KNN_MAX_K);
+  for (int b = 0; b < B; ++b) {
+    GF_CHECK_ARG(Ns[b] >= 1 && xyz[b] && seeds[b] && geo[b], "guidance_batch: scene %d: empty or null", b);
+    GF_CHECK_ARG(geodesic_edge_format(Ns[b]) == 1,
+                 "guidance_batch: scene %d has %d points, beyond the on-chip bitmaps of the batched kernel "
+                 "(use gf_guidance per scene)", b, Ns[b]);
+  }
+  BatchPlan p;
+  size_t fps_b[GEO_BATCH_MAX], knn_b[GEO_BATCH_MAX], edge_b[GEO_BATCH_MAX];
+  plan_batch_guidance(Ns, B, Q, k, &p, fps_b, knn_b, edge_b);
+  if (workspace == nullptr || workspace_bytes < p.total) {
+    set_error("guidance_batch: workspace too small (%zu bytes given, %zu needed)", workspace_bytes, p.total);
+    return GF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char *w = (char *)workspace;
+  ForkJoin *fj = nullptr;
+  int rc = get_fork_join(st, &fj);
+  if (rc) return rc;
+  stage_mark(ST_BEGIN, st);
+  const int lanes = B < LANES ? B : LANES;
+  GF_CUDA(cudaEventRecord(fj->fork, st));
+  for (int l = 0; l < lanes; ++l) {
+    if (!seeds_given) GF_CUDA(cudaStreamWaitEvent(fj->fps[l], fj->fork, 0));
+    if (l > 0) GF_CUDA(cudaStreamWaitEvent(fj->knn[l], fj->fork, 0));
+  }
+  GeoSceneDesc desc[GEO_BATCH_MAX];
+  int64_t *d_stats = stats ? (int64_t *)(w + p.stats) : nullptr;
+  if (d_stats) GF_CUDA(cudaMemsetAsync(d_stats, 0, 16 * (size_t)B, st));
+  // FPS first on every lane (the longest chains start first), then the graphs
+  if (!seeds_given)
+    for (int b = 0; b < B; ++b) {
+      rc = gf_furthest_point_sampling(xyz[b], 1, Ns[b], Q, seeds[b], w + p.per_scene[b * 3 + 0], fps_b[b],
+                                      fj->fps[b % lanes]);
+      if (rc) return rc;
+    }
+  for (int b = 0; b < B; ++b) {
+    const int l = b % lanes;
+    cudaStream_t ks = l == 0 ? st : fj->knn[l];
+    KnnGridBuffers gb;
+    rc = knn_grid_build(xyz[b], Ns[b], k, w + p.per_scene[b * 3 + 1], knn_b[b], ks, &gb);
+    if (rc) return rc;
+    KnnEdgeOut eo;
+    eo.radius = radius;
+    rc = geodesic_edge_buffers(w + p.per_scene[b * 3 + 2], edge_b[b], Ns[b], k, 1, &eo.tgt, &eo.len, &eo.slot_bits,
+                               &eo.enc);
+    if (rc) return rc;
+    rc = knn_grid_query(gb, nullptr, Ns[b], k, /*sqrt=*/1, nullptr, nullptr, nullptr, ks, &eo);
+    if (rc) return rc;
+    desc[b].tgt = eo.tgt, desc[b].len = eo.len, desc[b].seeds = seeds[b], desc[b].geo = geo[b];
+    desc[b].row_max = row_max ? row_max[b] : nullptr;
+    desc[b].stats = d_stats ? d_stats + 2 * b : nullptr;
+    desc[b].N = Ns[b], desc[b].Q = Q;
+  }
+  for (int l = 0; l < lanes; ++l) {
+    if (!seeds_given) {
+      GF_CUDA(cudaEventRecord(fj->join_fps[l], fj->fps[l]));
+      GF_CUDA(cudaStreamWaitEvent(st, fj->join_fps[l], 0));
+    }
+    if (l > 0) {
+      GF_CUDA(cudaEventRecord(fj->join_knn[l], fj->knn[l]));
+      GF_CUDA(cudaStreamWaitEvent(st, fj->join_knn[l], 0));
+    }
+  }
+  stage_mark(ST_KNN_DONE, st);
+  rc = geodesic_batch_launch(desc, B, k, max_step, w + p.scratch, p.scratch_bytes, st);
+  if (rc) return rc;
+  if (stats) GF_CUDA(cudaMemcpyAsync(stats, d_stats, 16 * (size_t)B, cudaMemcpyDeviceToDevice, st));
+  return GF_OK;
 }
 
 extern "C" size_t gf_guidance_host_workspace_bytes(int N, int Q, int k) {

@@ -26,55 +26,33 @@ constexpr int KNN_SCAN_BLOCKS = 512;
 constexpr int KNN_MAX_DIM = 1024;
 
 // ---- device-side grid description --------------------------------------------------------------
+// The control block (KnnCtl: KnnGrid + the scan states) is cleared by ONE cudaMemsetAsync per build; every field is
+// laid out so that zero is its initial value.
 struct KnnGrid {
   float ox, oy, oz;  // origin = bbox min
   float h, inv_h;
   float slack;  // safety margin of the termination test (absolute length)
   int dx, dy, dz, ncells;
-  uint32_t mm[6];                  // ordered-uint min xyz, max xyz
-  unsigned long long sum_sq;       // sum over cells of count^2 (occupancy estimate)
-  float tau;                       // target occupancy
+  uint32_t mm[6];             // max over the points of ~ord(v) for x,y,z (= inverted minimum), then of ord(v)
+  unsigned long long sum_sq;  // sum over cells of count^2 (occupancy estimate of the coarse pass)
+  unsigned done[2];           // last-block-done counters of the two kernels that end with a planning tail
+  unsigned pad_[2];
 };
-
-__global__ void knn_init_kernel(KnnGrid *g, float tau) {
-  g->mm[0] = g->mm[1] = g->mm[2] = 0xffffffffu;
-  g->mm[3] = g->mm[4] = g->mm[5] = 0u;
-  g->sum_sq = 0ull;
-  g->tau = tau;
-}
-
-__global__ void knn_bbox_kernel(const float *__restrict__ xyz, int N, KnnGrid *g) {
-  uint32_t lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      float v = __ldg(xyz + (size_t)i * 3 + a);
-      if (v == v && fabsf(v) <= 3.0e38f) {  // ignore NaN / inf for the box
-        uint32_t o = f2ord(v);
-        lo[a] = min(lo[a], o);
-        hi[a] = max(hi[a], o);
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    uint32_t l = __reduce_min_sync(0xffffffffu, lo[a]);
-    uint32_t h = __reduce_max_sync(0xffffffffu, hi[a]);
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(&g->mm[a], l);
-      atomicMax(&g->mm[3 + a], h);
-    }
-  }
-}
+struct KnnCtl {
+  KnnGrid g;
+  unsigned long long scan_state[KNN_SCAN_BLOCKS];  // bit 63 = published, low bits = the block's cell-count sum
+};
 
 // pass 0: coarse guess from the bounding-box volume; pass 1: rescale h so that the occupancy seen
 // by a point (sum c^2 / N, measured with the pass-0 grid) becomes the target tau.
-__global__ void knn_plan_kernel(KnnGrid *g, int N, int pass) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Runs in ONE thread, as the tail of the last block of the kernel that produced its inputs.
+__device__ void knn_plan(KnnGrid *g, int N, int pass, float tau, int cap) {
+  volatile KnnGrid *vg = g;  // the inputs were written by other blocks of the same launch
   float lo[3], ext[3], maxext = 0.f, maxabs = 0.f;
   for (int a = 0; a < 3; ++a) {
-    bool empty = g->mm[a] == 0xffffffffu && g->mm[3 + a] == 0u;
-    float l = empty ? 0.f : ord2f(g->mm[a]), hgh = empty ? 0.f : ord2f(g->mm[3 + a]);
+    const uint32_t mn = ~vg->mm[a], mx = vg->mm[3 + a];
+    bool empty = mn == 0xffffffffu && mx == 0u;
+    float l = empty ? 0.f : ord2f(mn), hgh = empty ? 0.f : ord2f(mx);
     lo[a] = l;
     ext[a] = hgh - l;
     maxext = fmaxf(maxext, ext[a]);
@@ -82,17 +60,15 @@ __global__ void knn_plan_kernel(KnnGrid *g, int N, int pass) {
   }
   if (!(maxext > 0.f)) maxext = 1.f;
   float h;
-  const int cap = pass == 0 ? KNN_PASS0_CELLS : KNN_MAX_CELLS;
   if (pass == 0) {
     float vol = 1.f;
     for (int a = 0; a < 3; ++a) vol *= fmaxf(ext[a], 1e-3f * maxext);
-    h = cbrtf(vol * g->tau / (float)(N > 0 ? N : 1));
+    h = cbrtf(vol * tau / (float)(N > 0 ? N : 1));
   } else {
-    float occ = (float)((double)g->sum_sq / (double)(N > 0 ? N : 1));
-    float f = sqrtf(g->tau / fmaxf(occ, 1e-3f));  // surface-like scaling (occupancy ~ h^2)
+    float occ = (float)((double)vg->sum_sq / (double)(N > 0 ? N : 1));
+    float f = sqrtf(tau / fmaxf(occ, 1e-3f));  // surface-like scaling (occupancy ~ h^2)
     f = fminf(fmaxf(f, 0.125f), 4.f);
-    h = g->h * f;
-    g->sum_sq = 0ull;
+    h = vg->h * f;
   }
   h = fmaxf(h, maxext * 1e-6f);
   h = fmaxf(h, maxext / (float)KNN_MAX_DIM);
@@ -117,6 +93,21 @@ __global__ void knn_plan_kernel(KnnGrid *g, int N, int pass) {
   g->slack = 1e-3f * h + 4e-6f * maxabs;
 }
 
+// true in every thread of the block that finished last (its view of the other blocks' results is ordered
+// by the fence / counter pair, as in the CUDA threadFenceReduction sample)
+__device__ __forceinline__ bool last_block_done(unsigned *counter) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    s_last = t == gridDim.x - 1;
+    __threadfence();
+  }
+  __syncthreads();
+  return s_last;
+}
+
 __device__ __forceinline__ int cell_coord(float v, float o, float inv_h, int dim) {
   float f = floorf((v - o) * inv_h);
   int c = (f >= 0.f) ? (f < (float)dim ? (int)f : dim - 1) : 0;  // NaN -> 0
@@ -128,15 +119,46 @@ __device__ __forceinline__ int cell_of(const KnnGrid &g, float x, float y, float
   return (cz * g.dy + cy) * g.dx + cx;
 }
 
-__global__ void knn_zero_cells_kernel(const KnnGrid *__restrict__ g, int *__restrict__ cell_count) {
-  const int n = g->ncells;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cell_count[i] = 0;
+// build kernel 1 of 5: bounding box (+ tail: coarse grid plan) and the zero fill of both cell tables
+__global__ void __launch_bounds__(256) knn_bbox_kernel(const float *__restrict__ xyz, int N, KnnGrid *g, float tau,
+                                                       int cap_coarse, int4 *__restrict__ zero_a, int n4_a,
+                                                       int4 *__restrict__ zero_b, int n4_b) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  const int4 z4 = make_int4(0, 0, 0, 0);
+  for (int i = gtid; i < n4_a; i += gsz) zero_a[i] = z4;
+  for (int i = gtid; i < n4_b; i += gsz) zero_b[i] = z4;
+  uint32_t lo[3] = {0u, 0u, 0u}, hi[3] = {0u, 0u, 0u};  // lo holds the maximum of ~ord = the inverted minimum
+  for (int i = gtid; i < N; i += gsz) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float v = __ldg(xyz + (size_t)i * 3 + a);
+      if (v == v && fabsf(v) <= 3.0e38f) {  // ignore NaN / inf for the box
+        uint32_t o = f2ord(v);
+        lo[a] = max(lo[a], ~o);
+        hi[a] = max(hi[a], o);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    uint32_t l = __reduce_max_sync(0xffffffffu, lo[a]);
+    uint32_t h = __reduce_max_sync(0xffffffffu, hi[a]);
+    if ((threadIdx.x & 31) == 0) {
+      if (l) atomicMax(&g->mm[a], l);
+      if (h) atomicMax(&g->mm[3 + a], h);
+    }
+  }
+  if (last_block_done(&g->done[0]) && threadIdx.x == 0) knn_plan(g, N, 0, tau, cap_coarse);
 }
 
-__global__ void knn_count_kernel(const float *__restrict__ xyz, int N, const KnnGrid *__restrict__ gp,
-                                 int *__restrict__ cell_count, int *__restrict__ cell_id,
-                                 int *__restrict__ slot_in_cell) {
+// build kernels 2 and 3: population of every cell.  The coarse pass (cell_id == nullptr) also accumulates
+// sum c^2 = sum over the points of (2 * slot + 1) from the slots its atomics return, and ends with the plan of
+// the final grid; the final pass records every point's cell and slot for the scatter.
+__global__ void __launch_bounds__(256) knn_count_kernel(const float *__restrict__ xyz, int N, KnnGrid *gp,
+                                                        int *__restrict__ cell_count, int *__restrict__ cell_id,
+                                                        int *__restrict__ slot_in_cell, float tau, int cap_fine) {
   const KnnGrid g = *gp;
+  unsigned long long acc = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     float x = __ldg(xyz + (size_t)i * 3), y = __ldg(xyz + (size_t)i * 3 + 1), z = __ldg(xyz + (size_t)i * 3 + 2);
     int c = cell_of(g, x, y, z);
@@ -144,65 +166,55 @@ __global__ void knn_count_kernel(const float *__restrict__ xyz, int N, const Knn
     if (cell_id) {
       cell_id[i] = c;
       slot_in_cell[i] = s;
+    } else {
+      acc += 2ull * (unsigned)s + 1ull;
     }
   }
-}
-
-__global__ void knn_occupancy_kernel(KnnGrid *g, const int *__restrict__ cell_count) {
-  const int n = g->ncells;
-  unsigned long long acc = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    unsigned long long c = (unsigned long long)cell_count[i];
-    acc += c * c;
-  }
+  if (cell_id) return;
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&g->sum_sq, acc);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&gp->sum_sq, acc);
+  if (last_block_done(&gp->done[1]) && threadIdx.x == 0) knn_plan(gp, N, 1, tau, cap_fine);
 }
 
-// ---- exclusive scan of the cell counts (three small kernels, sizes read from the device) -------
-__global__ void __launch_bounds__(256) knn_scan_a(const KnnGrid *__restrict__ g, const int *__restrict__ cnt,
-                                                  int *__restrict__ bsum) {
-  const int n = g->ncells;
-  const int chunk = (n + KNN_SCAN_BLOCKS - 1) / KNN_SCAN_BLOCKS;
-  const int b0 = blockIdx.x * chunk, b1 = min(n, b0 + chunk);
+// build kernel 4: exclusive scan of the cell populations in one launch.  Block b sums its chunk and publishes
+// the sum; its carry-in is the sum of the published sums of the blocks before it (they were scheduled earlier,
+// so waiting for them cannot deadlock); then it rescans its chunk and writes the cell starts.
+__global__ void __launch_bounds__(256) knn_scan_kernel(KnnCtl *ctl, const int *__restrict__ cnt,
+                                                       int *__restrict__ start, int N) {
+  const int n = ctl->g.ncells;
+  const int chunk = (((n + KNN_SCAN_BLOCKS - 1) / KNN_SCAN_BLOCKS) + 3) & ~3;
+  const int b0 = min(n, (int)blockIdx.x * chunk), b1 = min(n, b0 + chunk);
+  __shared__ int ws[8];
+  __shared__ int carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int acc = 0;
   for (int i = b0 + threadIdx.x; i < b1; i += 256) acc += cnt[i];
-  __shared__ int ws[8];
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  if (lane == 0) ws[warp] = acc;
+  __syncthreads();
+  volatile unsigned long long *state = ctl->scan_state;
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    state[blockIdx.x] = (1ull << 63) | (unsigned long long)(unsigned)t;
+  }
+  int pre = 0;
+  for (int j = threadIdx.x; j < (int)blockIdx.x; j += 256) {
+    unsigned long long v;
+    while (!((v = state[j]) >> 63)) __nanosleep(20);
+    pre += (int)(unsigned)(v & 0xffffffffull);
+  }
+  for (int o = 16; o; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+  __syncthreads();  // ws is reused
+  if (lane == 0) ws[warp] = pre;
   __syncthreads();
   if (threadIdx.x == 0) {
     int t = 0;
     for (int w = 0; w < 8; ++w) t += ws[w];
-    bsum[blockIdx.x] = t;
+    carry = t;
   }
-}
-
-__global__ void __launch_bounds__(KNN_SCAN_BLOCKS) knn_scan_b(int *__restrict__ bsum) {
-  __shared__ int s[KNN_SCAN_BLOCKS];
-  int v = bsum[threadIdx.x];
-  s[threadIdx.x] = v;
-  __syncthreads();
-  for (int o = 1; o < KNN_SCAN_BLOCKS; o <<= 1) {
-    int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
-    __syncthreads();
-    s[threadIdx.x] += t;
-    __syncthreads();
-  }
-  bsum[threadIdx.x] = s[threadIdx.x] - v;  // exclusive
-}
-
-__global__ void __launch_bounds__(256) knn_scan_c(const KnnGrid *__restrict__ g, const int *__restrict__ cnt,
-                                                  const int *__restrict__ bsum, int *__restrict__ start, int N) {
-  const int n = g->ncells;
-  const int chunk = (n + KNN_SCAN_BLOCKS - 1) / KNN_SCAN_BLOCKS;
-  const int b0 = blockIdx.x * chunk, b1 = min(n, b0 + chunk);
-  __shared__ int ws[8];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = bsum[blockIdx.x];
   if (blockIdx.x == 0 && threadIdx.x == 0) start[n] = N;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int t0 = b0; t0 < b1; t0 += 1024) {
     int i0 = t0 + threadIdx.x * 4;
     int c[4];
@@ -230,15 +242,14 @@ __global__ void __launch_bounds__(256) knn_scan_c(const KnnGrid *__restrict__ g,
   }
 }
 
+// build kernel 5: the points in cell order, each with its original index
 __global__ void knn_scatter_kernel(const float *__restrict__ xyz, int N, const int *__restrict__ cell_id,
                                    const int *__restrict__ slot_in_cell, const int *__restrict__ start,
-                                   float4 *__restrict__ sorted, int *__restrict__ order, int *__restrict__ rank) {
+                                   float4 *__restrict__ sorted) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     int pos = start[cell_id[i]] + slot_in_cell[i];
     float x = __ldg(xyz + (size_t)i * 3), y = __ldg(xyz + (size_t)i * 3 + 1), z = __ldg(xyz + (size_t)i * 3 + 2);
     sorted[pos] = make_float4(x, y, z, __int_as_float(i));
-    order[pos] = i;
-    rank[i] = pos;
   }
 }
 
@@ -267,6 +278,47 @@ struct TopK {
     }
   }
   __device__ __forceinline__ float kth_d2() const { return __uint_as_float((unsigned)(key[KT - 1] >> 32)); }
+  // The row of the propagation's edge table (gf_geodesic.cu: geo_pack_edges_kernel, same rule): neighbour
+  // 1 + e of the result as edge e if it may ever be used (sqrt(d2) <= radius, geodesic_utils.py:123,151),
+  // else an edge to the sentinel point N; padded with such edges to KP = 1 << slot_bits entries.
+  __device__ __forceinline__ void store_edges(int k, float radius, int N, int slot_bits, int enc,
+                                              int *__restrict__ tgt, float *__restrict__ len) const {
+    const int KP = 1 << slot_bits;
+    auto code = [&](int t) { return enc ? (int)((((unsigned)t >> 5) << 7) | ((unsigned)t & 31u)) : t; };
+    const int none = code(N);
+    if (k == KT && KP == KT) {  // the usual case (k a power of two): whole 16-byte stores
+#pragma unroll
+      for (int e0 = 0; e0 < KT; e0 += 4) {
+        int t[4];
+        float w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u;
+          t[u] = none, w[u] = 0.f;
+          if (e + 1 < KT) {
+            const unsigned long long kk = key[e + 1];
+            const float d = sqrtf(__uint_as_float((unsigned)(kk >> 32)));
+            if (kk != ~0ull && d <= radius) t[u] = code((int)(unsigned)(kk & 0xffffffffu)), w[u] = d;
+          }
+        }
+        reinterpret_cast<int4 *>(tgt)[e0 >> 2] = make_int4(t[0], t[1], t[2], t[3]);
+        reinterpret_cast<float4 *>(len)[e0 >> 2] = make_float4(w[0], w[1], w[2], w[3]);
+      }
+      return;
+    }
+#pragma unroll
+    for (int i = 0; i < KT; ++i) {
+      const int e = i - (KT - k) - 1;
+      if (e >= 0) {
+        const unsigned long long kk = key[i];
+        const float d = sqrtf(__uint_as_float((unsigned)(kk >> 32)));
+        const bool ok = kk != ~0ull && d <= radius;
+        tgt[e] = ok ? code((int)(unsigned)(kk & 0xffffffffu)) : none;
+        len[e] = ok ? d : 0.f;
+      }
+    }
+    for (int e = k - 1 > 0 ? k - 1 : 0; e < KP; ++e) tgt[e] = none, len[e] = 0.f;
+  }
   __device__ __forceinline__ void store(int k, bool do_sqrt, float *__restrict__ dist, long long *__restrict__ i64,
                                         int *__restrict__ i32) const {
 #pragma unroll
@@ -291,10 +343,15 @@ __global__ void __launch_bounds__(128)
     knn_grid_query_kernel(const KnnGrid *__restrict__ gp, const float4 *__restrict__ sorted,
                           const int *__restrict__ start, const float *__restrict__ queries, int nq, int k,
                           int do_sqrt, float *__restrict__ dist, long long *__restrict__ idx64,
-                          int *__restrict__ idx32) {
+                          int *__restrict__ idx32, const KnnEdgeOut eo) {
   const KnnGrid g = *gp;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nq) return;
+  if (eo.tgt && s == 0) {  // the sentinel row N: only edges to N
+    const int none = eo.enc ? (int)((((unsigned)nq >> 5) << 7) | ((unsigned)nq & 31u)) : nq;
+    for (int e = 0; e < (1 << eo.slot_bits); ++e)
+      eo.tgt[((size_t)nq << eo.slot_bits) + e] = none, eo.len[((size_t)nq << eo.slot_bits) + e] = 0.f;
+  }
   float qx, qy, qz;
   int row;
   if (queries == nullptr) {
@@ -363,8 +420,12 @@ __global__ void __launch_bounds__(128)
     float ms = mfd - g.slack;
     if (ms > 0.f && top.kth_d2() < ms * ms) break;
   }
-  top.store(k, do_sqrt != 0, dist ? dist + (size_t)row * k : nullptr, idx64 ? idx64 + (size_t)row * k : nullptr,
-            idx32 ? idx32 + (size_t)row * k : nullptr);
+  if (dist || idx64 || idx32)
+    top.store(k, do_sqrt != 0, dist ? dist + (size_t)row * k : nullptr, idx64 ? idx64 + (size_t)row * k : nullptr,
+              idx32 ? idx32 + (size_t)row * k : nullptr);
+  if (eo.tgt)  // self query only (nq == N): the propagation's edge rows, written straight from the registers
+    top.store_edges(k, eo.radius, nq, eo.slot_bits, eo.enc, eo.tgt + ((size_t)row << eo.slot_bits),
+                    eo.len + ((size_t)row << eo.slot_bits));
 }
 
 // ---- brute force (algo 1) -----------------------------------------------------------------------
@@ -403,20 +464,34 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---- host orchestration -------------------------------------------------------------------------
+// table sizes depend on N only (the workspace is sized before k is known)
+static int knn_cap_fine(int N) {
+  long long c = 8ll * N;
+  if (c < (1 << 18)) c = 1 << 18;
+  if (c > KNN_MAX_CELLS) c = KNN_MAX_CELLS;
+  return (int)c;
+}
+static int knn_cap_coarse(int N) {
+  int c = N < 4096 ? 4096 : N;
+  return c > KNN_PASS0_CELLS ? KNN_PASS0_CELLS : c;
+}
+
 size_t knn_grid_workspace_bytes(int N) {
   size_t b = 0;
-  b += align256(sizeof(KnnGrid));
-  b += align256(sizeof(int) * (size_t)(KNN_MAX_CELLS + 1)) * 2;  // cell_count, cell_start
-  b += align256(sizeof(int) * KNN_SCAN_BLOCKS);
-  b += align256(sizeof(int) * (size_t)N) * 4;  // cell_id, slot_in_cell, order, rank
+  b += align256(sizeof(KnnCtl));
+  b += align256(sizeof(int) * (size_t)knn_cap_coarse(N));
+  b += align256(sizeof(int) * (size_t)(knn_cap_fine(N) + 4)) * 2;  // cell_count, cell_start
+  b += align256(sizeof(int) * (size_t)N) * 2;                        // cell_id, slot_in_cell
   b += align256(sizeof(float4) * (size_t)N);
   return b + 1024;
 }
 
 template <int KT>
 static void launch_grid_query(const KnnGrid *g, const float4 *sorted, const int *start, const float *queries, int nq,
-                              int k, int do_sqrt, float *dist, long long *i64, int *i32, cudaStream_t st) {
-  knn_grid_query_kernel<KT><<<(nq + 127) / 128, 128, 0, st>>>(g, sorted, start, queries, nq, k, do_sqrt, dist, i64, i32);
+                              int k, int do_sqrt, float *dist, long long *i64, int *i32, const KnnEdgeOut &eo,
+                              cudaStream_t st) {
+  knn_grid_query_kernel<KT><<<(nq + 127) / 128, 128, 0, st>>>(g, sorted, start, queries, nq, k, do_sqrt, dist, i64, i32,
+                                                              eo);
 }
 template <int KT>
 static void launch_brute(const float *xyz, int N, const float *queries, int nq, int k, int do_sqrt, float *dist,
@@ -424,77 +499,63 @@ static void launch_brute(const float *xyz, int N, const float *queries, int nq, 
   knn_brute_kernel<KT><<<(nq + 127) / 128, 128, 0, st>>>(xyz, N, queries, nq, k, do_sqrt, dist, i64, i32);
 }
 
+// Five launches and one memset (round 1: thirteen launches): bbox + coarse plan | coarse count + final plan |
+// final count | scan | scatter.  Nothing returns to the host; grid dimensions are read from the device.
 int knn_grid_build(const float *xyz, int N, int k, void *workspace, size_t workspace_bytes, cudaStream_t st,
                    KnnGridBuffers *out) {
+  const int cap_fine = knn_cap_fine(N), cap_coarse = knn_cap_coarse(N);
   Arena a(workspace, workspace_bytes);
-  KnnGrid *g = a.take<KnnGrid>(1);
-  int *cell_count = a.take<int>(KNN_MAX_CELLS + 1);
-  int *cell_start = a.take<int>(KNN_MAX_CELLS + 1);
-  int *bsum = a.take<int>(KNN_SCAN_BLOCKS);
+  KnnCtl *ctl = a.take<KnnCtl>(1);
+  KnnGrid *g = &ctl->g;
+  int *coarse_count = a.take<int>(cap_coarse);
+  int *cell_count = a.take<int>(cap_fine + 4);
+  int *cell_start = a.take<int>(cap_fine + 4);
   int *cell_id = a.take<int>(N);
   int *slot = a.take<int>(N);
-  int *order = a.take<int>(N);
-  int *rank = a.take<int>(N);
   float4 *sorted = a.take<float4>(N);
   if (!a.ok) {
     set_error("knn: workspace too small (%zu bytes given, %zu needed)", workspace_bytes, knn_grid_workspace_bytes(N));
     return GF_ERR_WORKSPACE;
   }
   const int nb = num_sms() * 8;
-  static float tau_mul = -1.f;  // GF_KNN_TAU: experiment knob for the target cell occupancy (x k)
-  if (tau_mul < 0.f) {
+  static const float tau_mul = [] {  // GF_KNN_TAU: experiment knob for the target cell occupancy (x k)
     const char *e = getenv("GF_KNN_TAU");
-    tau_mul = e ? (float)atof(e) : 0.45f;
-    if (!(tau_mul > 0.f)) tau_mul = 0.45f;
-  }
+    const float v = e ? (float)atof(e) : 0.45f;
+    return v > 0.f ? v : 0.45f;
+  }();
   const float tau = fmaxf(2.f, tau_mul * (float)k);
-  knn_init_kernel<<<1, 1, 0, st>>>(g, tau);
+  const int npt = min(nb, (N + 255) / 256);
+  GF_CUDA(cudaMemsetAsync(ctl, 0, sizeof(KnnCtl), st));
+  knn_bbox_kernel<<<nb, 256, 0, st>>>(xyz, N, g, tau, cap_coarse, (int4 *)coarse_count, (cap_coarse + 3) / 4,
+                                      (int4 *)cell_count, (cap_fine + 4) / 4);
   GF_LAUNCHED();
-  knn_bbox_kernel<<<min(nb, (N + 255) / 256), 256, 0, st>>>(xyz, N, g);
+  knn_count_kernel<<<npt, 256, 0, st>>>(xyz, N, g, coarse_count, nullptr, nullptr, tau, cap_fine);
   GF_LAUNCHED();
-  // pass 0: coarse grid, only to measure the occupancy
-  knn_plan_kernel<<<1, 1, 0, st>>>(g, N, 0);
+  knn_count_kernel<<<npt, 256, 0, st>>>(xyz, N, g, cell_count, cell_id, slot, tau, cap_fine);
   GF_LAUNCHED();
-  knn_zero_cells_kernel<<<nb, 256, 0, st>>>(g, cell_count);
+  knn_scan_kernel<<<KNN_SCAN_BLOCKS, 256, 0, st>>>(ctl, cell_count, cell_start, N);
   GF_LAUNCHED();
-  knn_count_kernel<<<min(nb, (N + 255) / 256), 256, 0, st>>>(xyz, N, g, cell_count, nullptr, nullptr);
-  GF_LAUNCHED();
-  knn_occupancy_kernel<<<nb, 256, 0, st>>>(g, cell_count);
-  GF_LAUNCHED();
-  // pass 1: final grid
-  knn_plan_kernel<<<1, 1, 0, st>>>(g, N, 1);
-  GF_LAUNCHED();
-  knn_zero_cells_kernel<<<nb, 256, 0, st>>>(g, cell_count);
-  GF_LAUNCHED();
-  knn_count_kernel<<<min(nb, (N + 255) / 256), 256, 0, st>>>(xyz, N, g, cell_count, cell_id, slot);
-  GF_LAUNCHED();
-  knn_scan_a<<<KNN_SCAN_BLOCKS, 256, 0, st>>>(g, cell_count, bsum);
-  GF_LAUNCHED();
-  knn_scan_b<<<1, KNN_SCAN_BLOCKS, 0, st>>>(bsum);
-  GF_LAUNCHED();
-  knn_scan_c<<<KNN_SCAN_BLOCKS, 256, 0, st>>>(g, cell_count, bsum, cell_start, N);
-  GF_LAUNCHED();
-  knn_scatter_kernel<<<min(nb, (N + 255) / 256), 256, 0, st>>>(xyz, N, cell_id, slot, cell_start, sorted, order, rank);
+  knn_scatter_kernel<<<npt, 256, 0, st>>>(xyz, N, cell_id, slot, cell_start, sorted);
   GF_LAUNCHED();
   out->grid = g;
   out->cell_start = cell_start;
   out->sorted = sorted;
-  out->order = order;
-  out->rank = rank;
   return GF_OK;
 }
 
 int knn_grid_query(const KnnGridBuffers &b, const float *queries, int nq, int k, int do_sqrt, float *dist,
-                   long long *idx64, int *idx32, cudaStream_t st) {
+                   long long *idx64, int *idx32, cudaStream_t st, const KnnEdgeOut *edges) {
   const KnnGrid *g = (const KnnGrid *)b.grid;
+  KnnEdgeOut eo = {nullptr, nullptr, 0.f, 0, 0};
+  if (edges && queries == nullptr) eo = *edges;
   if (k <= 8)
-    launch_grid_query<8>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, st);
+    launch_grid_query<8>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, eo, st);
   else if (k <= 16)
-    launch_grid_query<16>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, st);
+    launch_grid_query<16>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, eo, st);
   else if (k <= 32)
-    launch_grid_query<32>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, st);
+    launch_grid_query<32>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, eo, st);
   else
-    launch_grid_query<64>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, st);
+    launch_grid_query<64>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, eo, st);
   GF_LAUNCHED();
   return GF_OK;
 }

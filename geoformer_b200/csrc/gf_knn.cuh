@@ -10,14 +10,21 @@ struct KnnGridBuffers {
   const void *grid;       // device KnnGrid
   const int *cell_start;  // (ncells+1) exclusive prefix of the cell populations
   const float4 *sorted;   // (N) points in cell order: x, y, z, bit-cast original index
-  const int *order;       // (N) order[sorted position] = original index
-  const int *rank;        // (N) rank[original index] = sorted position
+};
+
+// optional second output of the self query: the propagation's packed edge table (gf_geodesic.cuh)
+struct KnnEdgeOut {
+  int *tgt;    // (N + 1) << slot_bits
+  float *len;  // (N + 1) << slot_bits
+  float radius;
+  int slot_bits;
+  int enc;  // != 0: targets stored as (t >> 5) << 7 | (t & 31) (gf_geodesic.cu: geo_enc_target)
 };
 
 size_t knn_grid_workspace_bytes(int N);
 int knn_grid_build(const float *xyz, int N, int k, void *workspace, size_t workspace_bytes, cudaStream_t st,
                    KnnGridBuffers *out);
 int knn_grid_query(const KnnGridBuffers &b, const float *queries, int nq, int k, int do_sqrt, float *dist,
-                   long long *idx64, int *idx32, cudaStream_t st);
+                   long long *idx64, int *idx32, cudaStream_t st, const KnnEdgeOut *edges = nullptr);
 
 }  // namespace gf

@@ -8,6 +8,7 @@ import ctypes
 import torch
 
 from . import _capi as C
+from .guidance import BATCH_MAX_POINTS, geodesic_guidance_batch
 
 
 class FlatL2Index:
@@ -159,42 +160,34 @@ def cal_geodesic_vectorize(gpu_index, pre_enc_inds, locs_float_, batch_offset_, 
     own_index = gpu_index is None or isinstance(gpu_index, FlatL2Index)
     fused = own_index and (gpu_index is None or gpu_index.algo == 0)
     dev = locs_float_.device
-    # The scenes of a batch are independent (the reference loops over them, :98).  On the fused path they are
-    # spread over a few side streams so that one scene's latency-bound stages (the kNN grid build, a
-    # single wave of per-seed propagation CTAs) run under another scene's kernels: ~0.33 instead of ~0.55 ms
-    # per 100k-point scene.  Everything is joined back into the caller's stream before returning.
-    lanes = _side_streams(dev, min(batch_size, _MAX_SCENES_IN_FLIGHT)) if fused and batch_size > 1 and dev.type == "cuda" else []
-    cur = torch.cuda.current_stream(dev) if lanes else None
-    if lanes:
-        fork = torch.cuda.Event()
-        fork.record(cur)
-        for st in lanes:
-            st.wait_event(fork)
-    geo_dists = []
+    geo_dists = [None] * batch_size
+    batch = []  # (b, points, seeds) of the scenes that go through the batched library call
     for b in range(batch_size):
         start, end = int(offsets[b]), int(offsets[b + 1])
         seeds = pre_enc_inds[b][:n_queries]
-        locs_b = locs_float_[start:end].contiguous()
         if end - start == 0:
-            geo_dists.append(torch.empty((seeds.numel(), 0), dtype=torch.float32, device=dev))
+            geo_dists[b] = torch.empty((seeds.numel(), 0), dtype=torch.float32, device=dev)
             continue
-        if fused and lanes:
-            st = lanes[b % len(lanes)]
-            with torch.cuda.stream(st):
-                geo = geodesic_from_points(locs_b, seeds, neighbor, radius, max_step, ws_tag="guidance/lane%d" % (b % len(lanes)))
-            geo.record_stream(cur)  # allocated on the side stream, handed to the caller's
-            locs_b.record_stream(st)
-            seeds.record_stream(st)
+        locs_b = locs_float_[start:end].contiguous()
+        if fused and end - start <= BATCH_MAX_POINTS and seeds.numel() > 0:
+            batch.append((b, locs_b, seeds))
         elif fused:
-            geo = geodesic_from_points(locs_b, seeds, neighbor, radius, max_step)
+            geo_dists[b] = geodesic_from_points(locs_b, seeds, neighbor, radius, max_step)
         else:
             D, I = find_knn(gpu_index, locs_b, neighbor=neighbor)
-            geo = geodesic_from_graph(D, I, seeds, radius, max_step)
-        geo_dists.append(geo)
-    for st in lanes:
-        join = torch.cuda.Event()
-        join.record(st)
-        cur.wait_event(join)
+            geo_dists[b] = geodesic_from_graph(D, I, seeds, radius, max_step)
+    # The scenes of a batch are independent (the reference loops over them, :98): their graphs are built side by
+    # side and ALL their (scene, seed) pairs are propagated by one launch (gf_guidance_batch) -- the per-seed runs
+    # are chains of dependent latencies, so the GPU is only filled by many of them at once.
+    # Scenes with the same number of seeds share a call (pre_enc_inds is one (B, >= n_queries) tensor: all of them).
+    groups = {}
+    for b, locs_b, seeds in batch:
+        groups.setdefault(seeds.numel(), []).append((b, locs_b, seeds))
+    for q_n, items in groups.items():
+        _, geos = geodesic_guidance_batch([x for _, x, _ in items], q_n, neighbor, radius, max_step,
+                                          seeds=[s for _, _, s in items])
+        for (b, _, _), g in zip(items, geos):
+            geo_dists[b] = g
     return geo_dists
 
 

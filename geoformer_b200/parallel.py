@@ -60,32 +60,18 @@ def scene_parallel_guidance(scenes, n_queries, neighbor, radius, max_step, rank=
     if guidance_fn is not None or len(mine) < 2 or not scenes[mine[0]].is_cuda:
         fn = guidance_fn or _default_guidance
         return {s: fn(scenes[s], n_queries, neighbor, radius, max_step) for s in mine}
-    # this rank's scenes are independent as well: keep up to four in flight on side streams (the latency-bound
-    # stages of one scene run under the kernels of another), joined into the caller's stream at the end
-    from .geodesic_utils import _MAX_SCENES_IN_FLIGHT, _side_streams
-    from .guidance import geodesic_guidance
+    # this rank's scenes are independent as well: one batched library call builds their graphs side by side and
+    # propagates all their (scene, seed) pairs in one launch (scenes too large for it go one by one)
+    from .guidance import BATCH_MAX_POINTS, geodesic_guidance, geodesic_guidance_batch
 
-    dev = scenes[mine[0]].device
-    lanes = _side_streams(dev, min(len(mine), _MAX_SCENES_IN_FLIGHT))
-    cur = torch.cuda.current_stream(dev)
-    fork = torch.cuda.Event()
-    fork.record(cur)
+    small = [s for s in mine if scenes[s].size(0) <= BATCH_MAX_POINTS]
     out = {}
-    for i, s in enumerate(mine):
-        st = lanes[i % len(lanes)]
-        if i < len(lanes):
-            st.wait_event(fork)
-        with torch.cuda.stream(st):
-            seeds, geo = geodesic_guidance(scenes[s], n_queries, neighbor, radius, max_step,
-                                           ws_tag="guidance/lane%d" % (i % len(lanes)))
-        seeds.record_stream(cur)
-        geo.record_stream(cur)
-        scenes[s].record_stream(st)
-        out[s] = (seeds, geo)
-    for st in lanes:
-        join = torch.cuda.Event()
-        join.record(st)
-        cur.wait_event(join)
+    if small:
+        seeds, geos = geodesic_guidance_batch([scenes[s] for s in small], n_queries, neighbor, radius, max_step)
+        out.update({s: (seeds[i], geos[i]) for i, s in enumerate(small)})
+    for s in mine:
+        if s not in out:
+            out[s] = geodesic_guidance(scenes[s], n_queries, neighbor, radius, max_step)
     return out
 
 

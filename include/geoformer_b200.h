@@ -152,6 +152,18 @@ int gf_guidance_seeded(const float *xyz, int N, const int *seeds, int Q, int k, 
                        float *geo, float *knn_dist, int32_t *knn_idx32, int64_t *stats, float *row_max,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* A BATCH of scenes in one call: what cal_geodesic_vectorize does for the scenes of a batch (geodesic_utils.py:98
+ * loops over them one by one).  xyz[b] (Ns[b],3), seeds[b] (Q) i32 (written unless seeds_given), geo[b] (Q,Ns[b]),
+ * optional row_max[b] (Q); the pointer ARRAYS live in host memory, what they point to in device memory.
+ * stats: optional device (B,2) i64.  FPS and graph construction of the scenes run side by side on internal
+ * streams; the propagation of ALL scenes is ONE launch whose work items are (scene, seed) pairs, so that the
+ * GPU holds three to four times as many of these latency-bound runs as a scene alone offers.  B <= 16; every
+ * scene must fit the on-chip bitmaps (N <~ 860k), larger scenes go through gf_guidance one by one.          */
+size_t gf_guidance_batch_workspace_bytes(const int *Ns, int B, int Q, int k);
+int gf_guidance_batch(const float *const *xyz, const int *Ns, int B, int Q, int k, float radius, int max_step,
+                      int *const *seeds, int seeds_given, float *const *geo, float *const *row_max, int64_t *stats,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- one scene over several GPUs, split by seed blocks --------------------
  * New with this library (the reference is single-GPU, train.py:156-185).  Every rank holds the whole
  * (Q_total,N) matrix; rank r propagates the seeds [row0, row0+Q) and the propagation kernel itself stores

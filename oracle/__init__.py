@@ -42,6 +42,12 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n):
+    """OpenMP team size of the C routines (overrides an OMP_NUM_THREADS exported by a launcher)."""
+    lib().orc_set_num_threads(ctypes.c_int(int(n)))
+    return num_threads()
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

@@ -8,6 +8,10 @@ Plain torch ops on CPU tensors, following the reference line by line:
                               by the reference's own PositionEmbeddingCoordsSine)
 (only float32 add / sub / abs / max / sqrt / sign: every op is correctly rounded, so the CUDA
 kernels are expected to match bit for bit; the tests allow 1e-6 relative as SURVEY 8(c) states).
+PINNED: tests/golden/bias_golden.npz holds what the reference's own statements produce -- oracle/ref_bias.py
+cuts geoformer_fs.py:263-300 and :680-702 out of the reference source with `ast` and executes them unmodified
+(tests/golden/make_golden_bias.py); tests/test_oracle_golden.py asserts these functions == that fixture bit
+for bit, and tests/test_gpu_parity.py asserts the CUDA kernels == the fixture.
 """
 import numpy as np
 import torch
@@ -59,7 +63,8 @@ def mask_head_relative_coords(geo_dist, coords, fps_sampling_coords):
     M = torch.max(m)
     m = m.clone()
     m[m < 0] = M  # :276
-    m = torch.from_numpy(np.sqrt(m.numpy()))  # :277 (numpy's sqrt is correctly rounded, like CUDA's)
+    with np.errstate(invalid="ignore"):  # nothing reachable anywhere: the reference takes sqrt(-1) = NaN as well
+        m = torch.from_numpy(np.sqrt(m.numpy()))  # :277 (numpy's sqrt is correctly rounded, like CUDA's)
     m = m[:, None, None].expand(Q, N, 3)
     cond = (geo_dist < 0).unsqueeze(-1).expand(Q, N, 3)
     rel = rel.clone()

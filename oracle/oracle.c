@@ -44,6 +44,16 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* The timing legs of bench.py set the team size themselves: launchers such as torch.distributed.run
+ * export OMP_NUM_THREADS=1 to every rank, which would silently turn the host baseline into one core. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* lib/pointnet2/_ext_src/include/cuda_utils.h:15-21  opt_n_threads */
 static int opt_n_threads(int work_size) {
   int pow_2 = (int)(log((double)work_size) / log(2.0));

@@ -42,10 +42,20 @@ for N, room, Q, k, r, ms in cases:
 """
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2"])
-def test_geodesic_state_layouts_and_overflow(cuda_lib, oracle_lib, mode):
+# (GF_GEO_NOBITMAP, GF_GEO_ENC, GF_GEO_UNROLL, GF_GEO_THREADS): every kernel the size rule or a knob can select
+VARIANTS = [("0", "2", "2", "0"),     # the default: batched two-bitmap kernel, thread count by the number of seeds
+            ("0", "2", "1", "1024"), ("0", "2", "2", "512"), ("0", "2", "1", "256"), ("0", "2", "2", "256"),
+            ("0", "0", "2", "1024"),  # the per-scene template kernel with plain edge targets (round 1)
+            ("0", "0", "2", "512"),
+            ("1", "2", "2", "1024"),  # no on-chip state (the layout of scenes beyond ~860k points)
+            ("2", "2", "2", "1024")]  # visited bitmap only
+
+
+@pytest.mark.parametrize("mode,enc,unroll,threads", VARIANTS)
+def test_geodesic_state_layouts_and_overflow(cuda_lib, oracle_lib, mode, enc, unroll, threads):
     env = dict(os.environ)
     env["GF_GEO_NOBITMAP"] = mode  # 0 = size rule (both bitmaps here), 1 = no on-chip state, 2 = visited bitmap only
+    env["GF_GEO_ENC"], env["GF_GEO_UNROLL"], env["GF_GEO_THREADS"] = enc, unroll, threads
     out = subprocess.run([sys.executable, "-c", CHILD % ROOT], env=env, cwd=ROOT, capture_output=True, text=True,
                          timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]

@@ -27,6 +27,23 @@ def _tied_cloud(n, seed):
     return x
 
 
+def _check_knn_against_kdtree(x, rows, I_rows, D_rows, k):
+    """Independent exact kNN: scipy's cKDTree on the float64 copies of the points (a different algorithm, different
+    arithmetic, no code shared with the library or the oracle).  Tie-gap rule: position by position the float64
+    distance of OUR neighbour must equal the tree's within 2e-6 relative (fp32 rounding of d2 is ~3e-7), so an
+    index may differ from the tree's only where the two candidates are that close to a tie; the reported fp32
+    distances must be the float64 ones within 1e-6 relative.  Returns the number of rows whose index lists differ."""
+    from scipy.spatial import cKDTree
+
+    x64 = x.astype(np.float64)
+    d_ref, i_ref = cKDTree(x64).query(x64[rows], k=k)
+    d_ours = np.linalg.norm(x64[rows][:, None, :] - x64[I_rows.astype(np.int64)], axis=2)
+    np.testing.assert_allclose(d_ours, d_ref, rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(D_rows.astype(np.float64), d_ours, rtol=1e-6, atol=1e-9)
+    assert (d_ours[:, 1:] >= d_ours[:, :-1] - 2e-6 * d_ours[:, 1:] - 1e-9).all()
+    return int((I_rows.astype(np.int64) != i_ref).any(axis=1).sum())
+
+
 # ------------------------------------------------------------------------------------------ FPS
 @pytest.mark.parametrize("B,N,m", [(1, 1, 1), (1, 2, 2), (2, 7, 5), (1, 300, 64), (3, 511, 100), (1, 512, 128),
                                    (2, 1000, 256), (1, 5000, 512), (2, 20000, 300), (1, 70000, 128)])
@@ -370,9 +387,9 @@ def test_cal_geodesic_vectorize_batch_overlaps_scenes_and_stays_exact(dev):
 
 def test_full_size_config_c2(oracle_lib, dev):
     """BASELINE config 2 at full size (100k points, 256 seeds, k=16, radius 0.5, 32 levels) through the
-    fused entry point: seeds == oracle FPS; kNN rows == oracle on a 2000-row sample (and grid == brute
-    on all rows, test above); geodesic == oracle propagation on that graph, bit for bit; plus the
-    size-independent properties (seed entries 0, unreachable exactly -1, idempotence, reach 13.1 %)."""
+    fused entry point: seeds == oracle FPS; kNN == oracle on ALL rows and == an independent float64 k-d tree;
+    geodesic == oracle propagation on that graph, bit for bit; plus the size-independent properties (seed
+    entries 0, unreachable exactly -1, idempotence, reach 13.1 %)."""
     from geoformer_b200.guidance import geodesic_guidance
 
     xc = scene(100_000, 1234)
@@ -381,10 +398,13 @@ def test_full_size_config_c2(oracle_lib, dev):
     seeds2, geo2 = geodesic_guidance(x, 256, 16, 0.5, 32)
     assert torch.equal(seeds, seeds2) and torch.equal(geo, geo2)  # idempotent / deterministic
     assert np.array_equal(seeds.cpu().numpy(), oracle_lib.furthest_point_sampling(xc[None].numpy(), 256)[0])
-    rows = np.random.default_rng(0).choice(100_000, 2000, replace=False)
-    rD2, rI = oracle_lib.knn_sq(xc.numpy(), 16, xc.numpy()[rows])
-    assert np.array_equal(I.cpu().numpy()[rows], rI.astype(np.int32))
-    assert np.array_equal(D.cpu().numpy()[rows], np.sqrt(rD2))
+    # kNN: ALL 100k rows against the oracle (brute force, fp32, (d2, index) order: bit-exact) and against an
+    # independent float64 k-d tree (tie-gap rule in _check_knn_against_kdtree)
+    rD2, rI = oracle_lib.knn_sq(xc.numpy(), 16)
+    assert np.array_equal(I.cpu().numpy(), rI.astype(np.int32))
+    assert np.array_equal(D.cpu().numpy(), np.sqrt(rD2))
+    differing = _check_knn_against_kdtree(xc.numpy(), np.arange(100_000), I.cpu().numpy(), D.cpu().numpy(), 16)
+    assert differing < 100, differing  # only near-ties may be listed in another order (App. C scenes: a handful)
     ref, R, lev = oracle_lib.geodesic(D.cpu().numpy(), I.cpu().numpy().astype(np.int64), seeds.cpu().numpy(), 0.5, 32,
                                       return_stats=True)
     g = geo.cpu().numpy()
@@ -396,6 +416,34 @@ def test_full_size_config_c2(oracle_lib, dev):
     assert (geo[q, seeds.long()] == 0).all()
     assert (geo[geo < 0] == -1).all()
     assert abs(R / (256 * 100_000) - 0.131) < 2e-3
+
+
+def test_full_size_config_c4(oracle_lib, dev):
+    """BASELINE config 4 at full size (one 1M-point room, 512 seeds, k=16, radius 0.5, 32 levels): all 512 FPS
+    seeds == oracle (whole-GPU FPS variant); 20 000 sampled kNN rows == oracle and == the float64 k-d tree; the
+    propagation (the layout without on-chip bitmaps, which only scenes of this size select) == oracle
+    propagation on the GPU's graph for ALL 512 seeds, bit for bit; row maxima; statistics."""
+    from geoformer_b200.guidance import geodesic_guidance
+    from geoformer_b200.scenes import room
+
+    N, Q, k = 1_000_000, 512, 16
+    xc = room(N, 4321)
+    x = xc.to(dev)
+    rm = torch.zeros(Q, device=dev)
+    seeds, geo, D, I, stats = geodesic_guidance(x, Q, k, 0.5, 32, return_graph=True, return_stats=True, row_max=rm)
+    xn = xc.numpy()
+    assert np.array_equal(seeds.cpu().numpy(), oracle_lib.furthest_point_sampling(xn[None], Q)[0])
+    rows = np.sort(np.random.default_rng(4).choice(N, 20_000, replace=False))
+    In, Dn = I.cpu().numpy(), D.cpu().numpy()
+    rD2, rI = oracle_lib.knn_sq(xn, k, xn[rows])
+    assert np.array_equal(In[rows], rI.astype(np.int32))
+    assert np.array_equal(Dn[rows], np.sqrt(rD2))
+    assert _check_knn_against_kdtree(xn, rows, In[rows], Dn[rows], k) < 50
+    ref, R, lev = oracle_lib.geodesic(Dn, In.astype(np.int64), seeds.cpu().numpy(), 0.5, 32, return_stats=True)
+    g = geo.cpu().numpy()
+    assert np.array_equal(g, ref)
+    assert int(stats[0]) == R and int(stats[1]) == lev
+    assert np.array_equal(rm.cpu().numpy(), ref.max(axis=1))
 
 
 # ----------------------------------------------------------------------------------------- bias
@@ -442,19 +490,81 @@ def test_bias_epilogues(oracle_lib, dev):
 
 def test_guidance_runner_cuda_graph(dev):
     """The fused path (forked FPS stream included) captured into a CUDA graph replays to the same bits, also
-    when run() is handed another scene than the captured tensor."""
+    when run() is handed another scene than the one it was captured with; the caller's tensors are never
+    written (the graph reads a private staging buffer)."""
     from geoformer_b200.guidance import GuidanceRunner, geodesic_guidance
 
     xa, xb = scene(40000, 31).to(dev), scene(40000, 32).to(dev)
+    keep = {id(xa): xa.clone(), id(xb): xb.clone()}
+    want = {id(x): geodesic_guidance(x, 64, 16, 0.5, 20) for x in (xa, xb)}
+    torch.cuda.synchronize()
     r = GuidanceRunner(40000, 64, 16, 0.5, 20, device=dev, graph=True)
     side = torch.cuda.Stream(device=dev)
-    for x in (xa, xb, xa):
+    for x in (xa, xb, xa, xb):
         seeds, geo = r.run(x, side)
         side.synchronize()
-        ref_seeds, ref_geo = geodesic_guidance(x, 64, 16, 0.5, 20)
+        assert torch.equal(x, keep[id(x)]), "run() must not write the caller's points"
+        ref_seeds, ref_geo = want[id(x)]
         assert torch.equal(seeds, ref_seeds) and torch.equal(geo, ref_geo)
         assert torch.equal(r.row_max, ref_geo.max(dim=1).values)
-    assert r.launches_per_run == 17
+    assert not torch.equal(want[id(xa)][1], want[id(xb)][1])
+    # bbox+plan | coarse count+plan | count | scan | scatter | query (+ edge table) | propagation | FPS
+    assert r.launches_per_run == 8
+
+
+def test_guidance_batch_equals_per_scene_calls_and_oracle(oracle_lib, dev):
+    """gf_guidance_batch (graphs side by side, ONE propagation launch over all (scene, seed) pairs) on a ragged
+    batch: bit-identical to the per-scene call for every scene, to the oracle for two of them; seeds given or
+    sampled; row maxima and per-scene statistics."""
+    from geoformer_b200.guidance import geodesic_guidance, geodesic_guidance_batch
+
+    sizes = [20000, 31111, 12345, 50000, 777, 20000, 16384]
+    xs = [scene(n, 40 + i).to(dev) for i, n in enumerate(sizes)]
+    Q, k, r, ms = 40, 16, 0.5, 24
+    seeds, geos, stats, rmax = geodesic_guidance_batch(xs, Q, k, r, ms, return_stats=True, row_max=True)
+    for i, x in enumerate(xs):
+        s1, g1, st1 = geodesic_guidance(x, Q, k, r, ms, return_stats=True)
+        assert torch.equal(seeds[i], s1) and torch.equal(geos[i], g1), i
+        assert torch.equal(stats[i], st1), (i, stats[i], st1)
+        assert torch.equal(rmax[i], g1.max(dim=1).values), i
+    for i in (2, 4):
+        xn = xs[i].cpu().numpy()
+        rs = oracle_lib.furthest_point_sampling(xn[None], Q)[0]
+        rD, rI = oracle_lib.find_knn(xn, k)
+        assert np.array_equal(seeds[i].cpu().numpy(), rs)
+        assert np.array_equal(geos[i].cpu().numpy(), oracle_lib.geodesic(rD, rI, rs, r, ms))
+    # seeds given (the body of cal_geodesic_vectorize), more scenes than one library call takes (16)
+    many = [xs[i % len(xs)] for i in range(19)]
+    given = [torch.randperm(x.size(0), generator=torch.Generator().manual_seed(j))[:Q].int() for j, x in enumerate(many)]
+    _, geos2 = geodesic_guidance_batch(many, Q, k, r, ms, seeds=given)
+    from geoformer_b200.geodesic_utils import geodesic_from_points
+    for j, x in enumerate(many):
+        assert torch.equal(geos2[j], geodesic_from_points(x, given[j].to(dev), k, r, ms)), j
+
+
+def test_batch_guidance_runner_graph_and_stage_events(dev):
+    """BatchGuidanceRunner: plain and CUDA-graph replay give the bits of the per-scene call; the two stage events
+    that bracket the propagation launch are stamped by every replay (external event record nodes)."""
+    from geoformer_b200.guidance import BatchGuidanceRunner, geodesic_guidance
+
+    N, B, Q, k = 30000, 3, 48, 16
+    xa = [scene(N, 60 + i).to(dev) for i in range(B)]
+    xb = [scene(N, 70 + i).to(dev) for i in range(B)]
+    want = {id(x): geodesic_guidance(x, Q, k, 0.5, 20) for x in xa + xb}
+    side = torch.cuda.Stream(device=dev)
+    for graph in (False, True):
+        r = BatchGuidanceRunner(N, B, Q, k, 0.5, 20, device=dev, graph=graph, stage_events=True)
+        for xs in (xa, xb, xa):
+            seeds, geo = r.run(xs, side)
+            side.synchronize()
+            for b, x in enumerate(xs):
+                assert torch.equal(seeds[b], want[id(x)][0]) and torch.equal(geo[b], want[id(x)][1]), (graph, b)
+                assert torch.equal(r.row_max[b], want[id(x)][1].max(dim=1).values)
+            ms = r.propagation_ms()
+            assert ms is not None and 0.0 < ms < 50.0, ms
+        # per scene: bbox | coarse count | count | scan | scatter | query (+ edge table), FPS; one propagation launch
+        assert r.launches_per_run == 7 * B + 1, r.launches_per_run
+        r.close()
 
 
 def test_row_max_by_product(oracle_lib, dev):
@@ -487,6 +597,29 @@ def test_row_max_by_product(oracle_lib, dev):
     assert torch.equal(mask_head_relative_coords(geo, x2, sx, row_max=rm), mask_head_relative_coords(geo, x2, sx))
 
 
+def test_epilogues_match_reference_lines_fixture(dev):
+    """both epilogue kernels against tests/golden/bias_golden.npz = outputs of the reference's OWN statements
+    (geoformer_fs.py:263-300, :680-702 executed from source, oracle/ref_bias.py).  Bit-exact incl. the NaN case."""
+    import os
+
+    from geoformer_b200.bias import decoder_relative_pos, mask_head_relative_coords
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bias_golden.npz"))
+    T = lambda a: torch.from_numpy(np.array(a)).to(dev)  # noqa: E731
+    for i in range(int(g["n_mask"])):
+        geo = T(g["m%d_geo" % i])
+        out = mask_head_relative_coords(geo, T(g["m%d_coords" % i]), T(g["m%d_seed_xyz" % i]))
+        assert np.array_equal(out.cpu().numpy(), g["m%d_out" % i], equal_nan=True), i
+        out2 = mask_head_relative_coords(geo, T(g["m%d_coords" % i]), T(g["m%d_seed_xyz" % i]),
+                                         row_max=geo.max(dim=1).values.contiguous())
+        assert np.array_equal(out2.cpu().numpy(), g["m%d_out" % i], equal_nan=True), i
+    for i in range(int(g["n_dec"])):
+        B = int(g["d%d_B" % i])
+        out = decoder_relative_pos([T(g["d%d_geo%d" % (i, b)]) for b in range(B)], T(g["d%d_inds" % i]),
+                                   T(g["d%d_qry" % i]), T(g["d%d_ctx" % i]))
+        assert np.array_equal(out.cpu().numpy(), g["d%d_out" % i], equal_nan=True), i
+
+
 def test_decoder_fourier_embedding(dev):
     """geoformer_fs.py:680-712 fused (gather -> fill -> normalise -> 3x32 projection -> sin|cos) against the
     fixture produced by the reference's own PositionEmbeddingCoordsSine, and against the torch restatement
@@ -505,7 +638,10 @@ def test_decoder_fourier_embedding(dev):
     assert out.shape == (12, 40, 2, 64) and out.stride() == (40 * 64, 64, 12 * 40 * 64, 1)  # the reference's view
     torch.testing.assert_close(out.cpu().contiguous(), t["emb"], rtol=0, atol=2e-5)
     # model shapes: B=1, Q=256 queries, C=2048 contexts, d_pos=64; ragged context count and a narrower embedding too
-    for Q, Cn, d_pos, nch in ((256, 2048, 64, None), (37, 301, 64, None), (16, 100, 96, 64)):
+    # ... and embeddings whose half width d_out is below 32 or not a multiple of 32 (dec_dim = 32 -> d_out = 16,
+    # num_channels = 96 -> d_out = 48): lanes without a frequency must still take part in the warp's shuffles
+    for Q, Cn, d_pos, nch in ((256, 2048, 64, None), (37, 301, 64, None), (16, 100, 96, 64), (19, 77, 32, None),
+                              (23, 130, 96, None), (8, 33, 128, 96)):
         gen = torch.Generator().manual_seed(Q)
         N = 20000
         geo = torch.rand(Q, N, generator=gen) * 4.0

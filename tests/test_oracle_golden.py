@@ -189,3 +189,51 @@ def test_oracle_fourier_embedding_matches_reference_module_fixture():
     # the [sin | cos] halves are consistent
     s, c = emb[..., :32], emb[..., 32:]
     torch.testing.assert_close(s * s + c * c, torch.ones_like(s), rtol=0, atol=1e-5)
+
+
+def _bias_golden():
+    import torch
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bias_golden.npz"))
+    return g, (lambda a: torch.from_numpy(np.array(a)))
+
+
+def test_bias_oracle_matches_reference_lines_fixture():
+    """oracle/bias.py against tests/golden/bias_golden.npz = outputs of the reference's OWN epilogue statements
+    (geoformer_fs.py:263-300 and :680-702, executed from source by oracle/ref_bias.py).  Bit-exact, NaN included
+    (a matrix with nothing reachable makes the reference take sqrt(-1))."""
+    import torch
+
+    from oracle import bias as obias
+
+    g, T = _bias_golden()
+    assert tuple(g["mask_lines"]) == (263, 300) and tuple(g["dec_lines"]) == (680, 702)
+    for i in range(int(g["n_mask"])):
+        out = obias.mask_head_relative_coords(T(g["m%d_geo" % i]), T(g["m%d_coords" % i]), T(g["m%d_seed_xyz" % i]))
+        assert np.array_equal(out.numpy(), g["m%d_out" % i], equal_nan=True), i
+    for i in range(int(g["n_dec"])):
+        B = int(g["d%d_B" % i])
+        geos = [T(g["d%d_geo%d" % (i, b)]) for b in range(B)]
+        out = obias.decoder_relative_pos(geos, T(g["d%d_inds" % i]), T(g["d%d_qry" % i]), T(g["d%d_ctx" % i]))
+        assert np.array_equal(out.numpy(), g["d%d_out" % i], equal_nan=True), i
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/model/geoformer/geoformer_fs.py"),
+                    reason="the reference tree only exists in the build container")
+def test_bias_fixture_is_what_the_reference_lines_produce_today():
+    """regenerates the fixture's outputs from the reference source in this container (guards against a stale file)"""
+    import torch
+
+    from oracle import ref_bias
+
+    g, T = _bias_golden()
+    mask_fn, _ = ref_bias.load_mask_heads_forward()
+    dec_fn, _ = ref_bias.load_decoder_relative_pos()
+    for i in range(int(g["n_mask"])):
+        out = mask_fn(T(g["m%d_geo" % i]), T(g["m%d_coords" % i]), T(g["m%d_seed_xyz" % i]))
+        assert np.array_equal(out.numpy(), g["m%d_out" % i], equal_nan=True)
+    for i in range(int(g["n_dec"])):
+        B = int(g["d%d_B" % i])
+        out = dec_fn([T(g["d%d_geo%d" % (i, b)]) for b in range(B)], T(g["d%d_inds" % i]), T(g["d%d_qry" % i]),
+                     T(g["d%d_ctx" % i]))
+        assert np.array_equal(out.numpy(), g["d%d_out" % i], equal_nan=True)
