@@ -5,17 +5,23 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-One step = one pass of the hot path (FPS seeds -> kNN graph -> geodesic maps) over one synthetic
-scene of the workload (default c2: 100k points, 256 seeds, k=16, radius 0.5, 32 levels).
-  value     whole-job maps/s with the scenes already resident in HBM (CUDA events, max over ranks)
+One step = one pass of the hot path (FPS seeds -> kNN graph -> geodesic maps) over one synthetic scene of the
+workload (default c2: 100k points, 256 seeds, k=16, radius 0.5, 32 levels).  The library call is batched like the
+reference's own (cal_geodesic_vectorize takes a batch of scenes): --batch B scenes per call, so K steps are K/B
+calls, replayed as CUDA graphs on two alternating streams (the FPS / graph construction of one batch runs under
+the propagation of the previous one).
+  value     whole-job maps/s with the scenes already resident in HBM: EXACTLY K steps between two CUDA events,
+            barrier + synchronize on both sides, max over ranks; the K-step region is repeated (--repeats) and the
+            MEDIAN region is reported, all regions listed in `repeats_ms`
   e2e       the same through the host-buffer C-ABI call gf_guidance_host: pinned host points in,
             seeds + maps back in pinned host memory, copies inside the timed region
-  roofline  the propagation kernel (geo_seed_bfs_kernel): algorithmic bytes of SURVEY 8(d) / its live
-            CUDA-event duration in the timed region, against the measured HBM peak (MEASURED_PEAKS.json);
-            `*_alone` = the same kernel timed in a short serial pass (one scene in flight)
+  roofline  the propagation kernel (geo_bfs_batch_kernel, one launch per batch): algorithmic bytes of SURVEY 8(d)
+            x the scenes of a launch / its CUDA-event duration inside the timed region (external event nodes of the
+            replayed graphs), against the measured HBM peak (MEASURED_PEAKS.json); `*_alone` = the same launch
+            with nothing else running
   cpu_baseline  the CPU oracle port (oracle/) on this box's host cores, bounded sample (N=1 only)
---impl reference times that CPU port as the reference arm (the reference's own torch code cannot
-travel to the GPU box and its kNN is faiss-gpu, absent everywhere).
+--impl reference times that CPU port as the reference arm on all host cores (the reference's own torch code
+cannot travel to the GPU box and its kNN is faiss-gpu, absent everywhere).
 """
 import argparse
 import ctypes
@@ -29,22 +35,27 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+N_SCENES = 8  # rotating scenes per rank (both arms)
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
     ap.add_argument("--max-step", type=int, default=None, help="override the workload's level bound")
-    ap.add_argument("--streams", type=int, default=4,
-                    help="scenes in flight on the device (CUDA streams alternated step by step); 1 = strictly serial")
+    ap.add_argument("--batch", type=int, default=4, help="scenes per library call (reduced to a divisor of --steps)")
+    ap.add_argument("--repeats", type=int, default=0, help="repetitions of the K-step timed region (0 = automatic)")
+    ap.add_argument("--runners", type=int, default=2, help="batches in flight (alternating CUDA streams)")
+    ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     ap.add_argument("--seed-sharded", default=None, choices=["nccl", "fused"],
                     help="ONE scene split by seed blocks over the ranks (SURVEY 8(e), strong scaling): row blocks "
                          "exchanged by an NCCL all-gather, or stored into the peers by the propagation kernel itself")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip epilogues / eval setting / model setting records")
     return ap.parse_args()
 
 
@@ -64,6 +75,21 @@ def make_scene(cfg, index):
     return gen(cfg["n"], cfg["seed"] + index)
 
 
+def config_block(cfg, args):
+    """identical in both arms: only what defines the workload"""
+    n_sc = N_SCENES if cfg["n"] <= 200_000 else 2
+    return {"workload": "%s: %s(n=%d), Q=%d seeds, k=%d, radius=%.3g, max_step=%d" % (
+        args.workload, cfg["gen"], cfg["n"], cfg["Q"], cfg["k"], cfg["radius"], cfg["max_step"]),
+        "N": cfg["n"], "Q": cfg["Q"], "k": cfg["k"], "radius": cfg["radius"], "max_step": cfg["max_step"],
+        "inputs": "%d rotating synthetic scenes per rank (generator seeds %d..%d), %.0f MB of maps each: far above "
+                  "the 126 MB L2 in total, no explicit flush" % (n_sc, cfg["seed"], cfg["seed"] + n_sc - 1,
+                                                                 4e-6 * cfg["Q"] * cfg["n"])}
+
+
+def n_scenes_for(cfg):
+    return N_SCENES if cfg["n"] <= 200_000 else 2
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -74,21 +100,22 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """per-launch DRAM bytes of the level kernel from the committed ncu capture, if any"""
-    p = os.path.join(ROOT, "profiles", "geo_levels_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
+def ncu_traffic(workload_name, max_step, batch):
+    """per-launch DRAM bytes of the propagation kernel from the committed ncu capture of the same configuration
+    (profiles/geo_traffic.json: {"<workload>:<max_step>:B<batch>": {"dram_bytes_per_launch": .., "captured": ..}})"""
+    p = os.path.join(ROOT, "profiles", "geo_traffic.json")
+    try:
+        rec = json.load(open(p)).get("%s:%d:B%d" % (workload_name, max_step, batch))
+        return (rec["dram_bytes_per_launch"], rec.get("captured")) if rec else (None, None)
+    except Exception:
+        return None, None
 
 
 class ClockSampler(threading.Thread):
-    """samples SM clock and throttle reasons of one GPU through NVML while the timed region runs"""
+    """samples SM clock and throttle reasons of one GPU through NVML while the timed regions run (100 Hz: the
+    timed loop only replays a few graphs per region, the poller does not compete with it for the driver)"""
 
-    def __init__(self, index, period=0.004):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -136,58 +163,68 @@ class ClockSampler(threading.Thread):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "window": "the repeated timed regions, sampled at %.0f Hz" % (1.0 / self.period)}
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU port (oracle) timing: used for cpu_baseline and for --impl reference.  The ONLY place bench.py
 # touches oracle/.
 # ------------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 class CpuPort:
-    def __init__(self, cfg, budget_s):
+    """FPS + exact kNN + propagation of whole scenes on the host cores (OpenMP team = every core this process may
+    run on, set explicitly: torch.distributed.run exports OMP_NUM_THREADS=1).  Nothing is sampled or extrapolated
+    unless a whole scene would take longer than `max_step_s` (few-core hosts); then the kNN query rows are cut to
+    a prefix and the record says so."""
+
+    def __init__(self, cfg, max_step_s=12.0):
         import numpy as np
 
         import oracle
 
         oracle.build()
         self.np, self.oracle, self.cfg = np, oracle, cfg
-        self.x = make_scene(cfg, 0).numpy()
+        self.cores = oracle.set_num_threads(host_cores())
+        self.xs = [make_scene(cfg, s).numpy() for s in range(n_scenes_for(cfg))]
         self.N, self.Q, self.k = cfg["n"], cfg["Q"], cfg["k"]
-        self.cores = oracle.num_threads()
-        # probe the kNN rate on a small row sample, then size the per-step sample to the budget
-        rows = min(self.N, 1024)
+        rows = min(self.N, 2048)
         t0 = time.perf_counter()
-        oracle.knn_sq(self.x, self.k, self.x[:rows])
-        rate = (time.perf_counter() - t0) / rows  # seconds per query row
-        t0 = time.perf_counter()
-        self.seeds = oracle.furthest_point_sampling(self.x[None], self.Q)[0]
-        self.t_fps_probe = time.perf_counter() - t0
-        knn_budget = max(0.2, budget_s - self.t_fps_probe - 0.3)
-        self.rows = int(min(self.N, max(1024, knn_budget / max(rate, 1e-9))))
+        oracle.knn_sq(self.xs[0], self.k, self.xs[0][:rows])
+        est = (time.perf_counter() - t0) / rows * self.N
+        self.rows = self.N if est <= max_step_s else max(2048, int(self.N * max_step_s / est))
         self.full = self.rows >= self.N
-        # the propagation needs the whole graph; when the kNN is sampled it is built once, untimed
-        self.D, self.I = oracle.find_knn(self.x, self.k)
-        self.sample = ("full scene per step" if self.full else
-                       "per step: FPS full + kNN on %d of %d query rows (time scaled x%.2f) + geodesic full, "
-                       "graph for the propagation prebuilt untimed" % (self.rows, self.N, self.N / self.rows))
+        self.graph = None
+        if not self.full:  # the propagation needs the whole graph: built once, untimed
+            self.graph = [oracle.find_knn(x, self.k) for x in self.xs[:1]]
+        self.sample = ("whole scenes: FPS + exact kNN of all %d rows + propagation, %d OpenMP threads" % (self.N, self.cores)
+                       if self.full else
+                       "FPS whole + kNN on the first %d of %d query rows (NOT extrapolated: the step is shorter than a "
+                       "whole scene) + propagation whole on a prebuilt graph, %d OpenMP threads" % (self.rows, self.N, self.cores))
 
-    def step(self):
-        """returns the (extrapolated) seconds one full scene takes on the host cores"""
+    def step(self, i=0):
+        """seconds of one step and the per-stage split"""
         o, np = self.oracle, self.np
+        x = self.xs[i % len(self.xs)] if self.full else self.xs[0]
         t0 = time.perf_counter()
-        seeds = o.furthest_point_sampling(self.x[None], self.Q)[0]
+        seeds = o.furthest_point_sampling(x[None], self.Q)[0]
         t1 = time.perf_counter()
         if self.full:
-            D2, I = o.knn_sq(self.x, self.k)
+            D2, I = o.knn_sq(x, self.k)
             D = np.sqrt(D2)
         else:
-            o.knn_sq(self.x, self.k, self.x[: self.rows])
-            D, I = self.D, self.I
+            o.knn_sq(x, self.k, x[: self.rows])
+            D, I = self.graph[0]
         t2 = time.perf_counter()
         o.geodesic(D, I, seeds, self.cfg["radius"], self.cfg["max_step"])
         t3 = time.perf_counter()
-        t_knn = (t2 - t1) * (1.0 if self.full else self.N / self.rows)
-        return (t1 - t0) + t_knn + (t3 - t2), {"fps_s": t1 - t0, "knn_s": t_knn, "geodesic_s": t3 - t2}
+        return t3 - t0, {"fps_s": t1 - t0, "knn_s": t2 - t1, "geodesic_s": t3 - t2}
 
 
 def run_reference(args):
@@ -195,14 +232,13 @@ def run_reference(args):
     if rank != 0:
         return 0
     cfg = workload(args)
-    budget = min(3.0, 150.0 / max(1, args.steps + args.warmup))
-    port = CpuPort(cfg, budget)
-    for _ in range(args.warmup):
-        port.step()
+    port = CpuPort(cfg)
+    for i in range(args.warmup):
+        port.step(i)
     t_wall0 = time.perf_counter()
     total, parts = 0.0, []
-    for _ in range(args.steps):
-        t, p = port.step()
+    for i in range(args.steps):
+        t, p = port.step(args.warmup + i)
         total += t
         parts.append(p)
     wall = time.perf_counter() - t_wall0
@@ -212,23 +248,15 @@ def run_reference(args):
         "impl": "reference", "metric": "geodesic maps/sec", "value": value, "unit": "maps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_block(cfg, args, extra={"arm": "CPU port of the reference path (oracle/oracle.c, OpenMP)"}),
+        "config": config_block(cfg, args),
+        "arm": "CPU port of the reference path (oracle/oracle.c, OpenMP) on rank 0's host cores",
         "cpu_baseline": {"value": value, "unit": "maps/s", "cores": port.cores, "kind": "port", "sample": port.sample},
         "e2e": {"value": value, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "stage_s": {k: statistics.mean(p[k] for p in parts) for k in parts[0]} if parts else {},
-        "wall_s": wall,
+        "whole_scene_per_step": port.full, "wall_s": wall,
     }
     print(json.dumps(line), flush=True)
     return 0
-
-
-def config_block(cfg, args, extra=None):
-    c = {"workload": "%s: %s(n=%d), Q=%d seeds, k=%d, radius=%.3g, max_step=%d" % (
-        args.workload, cfg["gen"], cfg["n"], cfg["Q"], cfg["k"], cfg["radius"], cfg["max_step"]),
-        "N": cfg["n"], "Q": cfg["Q"], "k": cfg["k"], "radius": cfg["radius"], "max_step": cfg["max_step"]}
-    if extra:
-        c.update(extra)
-    return c
 
 
 def bind_to_gpu_numa_node(local):
@@ -254,14 +282,54 @@ def bind_to_gpu_numa_node(local):
 
 
 # ------------------------------------------------------------------------------------------------
+def seed_sharded_record(cfg4, mode, steps, dist, dev, rank, world):
+    """One c4 scene split by seed blocks over the ranks; returns the sub-record on rank 0."""
+    import torch
+
+    from geoformer_b200.parallel import SeedShardedRows, seed_sharded_guidance, seed_sharded_guidance_fused
+
+    N, Q, k = cfg4["n"], cfg4["Q"], cfg4["k"]
+    x = make_scene(cfg4, 0).to(dev)
+    rows = SeedShardedRows(Q, N) if mode == "fused" else None
+
+    def step():
+        if rows is not None:
+            return seed_sharded_guidance_fused(x, Q, k, cfg4["radius"], cfg4["max_step"], rows)
+        return seed_sharded_guidance(x, Q, k, cfg4["radius"], cfg4["max_step"])
+
+    for _ in range(3):
+        out = step()
+    torch.cuda.synchronize(dev)
+    checksum = float(out[1].double().sum().item())
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cs = torch.tensor([checksum], device=dev, dtype=torch.float64)
+    lo, hi = cs.clone(), cs.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if rows is not None:
+        rows.close()
+    del x
+    return {"workload": "c4: room(n=%d), Q=%d, k=%d" % (N, Q, k), "exchange": mode, "world": world,
+            "ms_per_scene": float(t.item()) / steps, "steps": steps,
+            "maps_per_s": Q / (float(t.item()) / steps * 1e-3),
+            "result_identical_on_all_ranks": bool(lo.item() == hi.item()), "checksum": checksum}
+
+
 def run_seed_sharded(args):
     """One scene, seed blocks per rank (strong scaling).  Not the driver's default line: an extra mode
     for the c4 row of SURVEY 8(e); prints the same JSON shape."""
     import torch
     import torch.distributed as dist
-
-    from geoformer_b200 import _capi as C
-    from geoformer_b200.parallel import SeedShardedRows, seed_sharded_guidance, seed_sharded_guidance_fused
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -272,63 +340,36 @@ def run_seed_sharded(args):
     os.environ.setdefault("MASTER_PORT", "29511")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     cfg = workload(args)
-    N, Q, k = cfg["n"], cfg["Q"], cfg["k"]
-    x = make_scene(cfg, 0).to(dev)
-    rows = SeedShardedRows(Q, N) if args.seed_sharded == "fused" else None
-
-    def step():
-        if rows is not None:
-            return seed_sharded_guidance_fused(x, Q, k, cfg["radius"], cfg["max_step"], rows)
-        return seed_sharded_guidance(x, Q, k, cfg["radius"], cfg["max_step"])
-
-    for _ in range(max(3, args.warmup)):
-        out = step()
-    torch.cuda.synchronize(dev)
-    checksum = float(out[1].double().sum().item())
     K = min(args.steps, 32)
     sampler = ClockSampler(local)
-    dist.barrier()
-    torch.cuda.synchronize(dev)
     sampler.start()
-    C.reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        step()
-    e1.record()
-    dist.barrier()
-    torch.cuda.synchronize(dev)
-    launches = C.launch_count()
+    rec = seed_sharded_record(cfg, args.seed_sharded, K, dist, dev, rank, world)
     clocks = sampler.stop()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / K
-    cs = torch.tensor([checksum], device=dev, dtype=torch.float64)
-    lo, hi = cs.clone(), cs.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({
-            "metric": "geodesic maps/sec", "value": Q / (ms_step * 1e-3), "unit": "maps/s", "n_gpus": world, "steps": K,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_block(cfg, args, extra={
-                "parallelism": "seed-sharded x%d, exchange: %s" % (world, args.seed_sharded),
-                "l2": "result matrix %.0f MB per rank (> 126 MB L2)" % (4.0 * Q * N / 1e6)}),
-            "gpu_launches": launches, "clocks": clocks,
-            "result_identical_on_all_ranks": bool(lo.item() == hi.item()), "checksum": checksum,
+            "metric": "geodesic maps/sec", "value": rec["maps_per_s"], "unit": "maps/s", "n_gpus": world, "steps": K,
+            "warmup": 3, "ms_per_step": rec["ms_per_scene"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(cfg, args),
+            "parallelism": "seed-sharded x%d, exchange: %s" % (world, args.seed_sharded), "clocks": clocks,
+            "result_identical_on_all_ranks": rec["result_identical_on_all_ranks"], "checksum": rec["checksum"],
         }), flush=True)
-    if rows is not None:
-        rows.close()
     dist.destroy_process_group()
     return 0
+
+
+def pick_batch(K, want):
+    """largest batch size <= want that divides K (K steps must be whole calls)"""
+    for b in range(max(1, min(want, 16)), 0, -1):
+        if K % b == 0:
+            return b
+    return 1
 
 
 def run_ours(args):
     import torch
 
     from geoformer_b200 import _capi as C
-    from geoformer_b200.guidance import GuidanceRunner, HostGuidance
+    from geoformer_b200.guidance import BATCH_MAX_POINTS, BatchGuidanceRunner, GuidanceRunner, HostGuidance
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -347,204 +388,174 @@ def run_ours(args):
 
     cfg = workload(args)
     N, Q, k = cfg["n"], cfg["Q"], cfg["k"]
+    K = args.steps
     L = C.lib()
-    # rotating scenes: per-scene footprint (points + workspace + maps) x S is far above the 126 MB L2
-    per_scene = L.gf_guidance_workspace_bytes(N, Q, k) + 4 * Q * N + 12 * N
-    S = int(max(2, min(8, (6 << 30) // max(per_scene, 1))))
+    batched = N <= BATCH_MAX_POINTS
+    B = pick_batch(K, args.batch) if batched else 1
+    calls = K // B
+    n_run = max(1, min(args.runners, calls))
+    S = n_scenes_for(cfg)
     # every rank runs the same S scenes: weak scaling with an identical per-GPU workload (with different scenes
     # per rank the max-over-ranks time measures which rank drew the heaviest scenes: +-10 % between scene sets)
     scenes_host = [make_scene(cfg, s) for s in range(S)]
     xs = [x.to(dev) for x in scenes_host]
-    runners = [GuidanceRunner(N, Q, k, cfg["radius"], cfg["max_step"], device=dev) for _ in range(S)]
     stream = torch.cuda.current_stream(dev)
+    side = [torch.cuda.Stream(device=dev) for _ in range(n_run)]
+
+    if batched:
+        runners = [BatchGuidanceRunner(N, B, Q, k, cfg["radius"], cfg["max_step"], device=dev,
+                                       graph=not args.no_graph, stage_events=True) for _ in range(n_run)]
+        for i, r in enumerate(runners):  # runner i always holds the same B scenes: together they rotate over all S
+            r.load([xs[(i * B + b) % S] for b in range(B)], side[i])
+    else:  # scenes beyond the on-chip bitmaps (c4): one scene per call, plain launches
+        runners = [GuidanceRunner(N, Q, k, cfg["radius"], cfg["max_step"], device=dev) for _ in range(n_run)]
+
+    def launch(c):
+        r, st = runners[c % n_run], side[c % n_run]
+        if batched:
+            r.replay(st)
+        else:
+            r.run(xs[c % S], st)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(max(3, args.warmup)):
-        runners[i % S].run(xs[i % S])
+    # warm-up: W steps, and at least three calls of every (runner, stream) pair: graph capture, auxiliary streams
+    # and events, kernel attributes and the clocks are all settled before the first timed region
+    warm_calls = max(-(-max(3, args.warmup) // B), 3 * n_run)
+    for c in range(warm_calls):
+        launch(c)
     torch.cuda.synchronize(dev)
-    reach = [int(r.stats[0].item()) for r in runners[: min(S, max(3, args.warmup))]]
-    levels = [int(r.stats[1].item()) for r in runners[: min(S, max(3, args.warmup))]]
+    if batched:
+        reach = [int(v) for r in runners for v in r.stats[:, 0].tolist()]
+        levels = [int(v) for r in runners for v in r.stats[:, 1].tolist()]
+        launches_per_call = runners[0].launches_per_run
+    else:
+        reach = [int(r.stats[0].item()) for r in runners]
+        levels = [int(r.stats[1].item()) for r in runners]
+        C.reset_launch_count()
+        launch(0)
+        torch.cuda.synchronize(dev)
+        launches_per_call = C.launch_count()
 
-    # ---- device-resident timed region -----------------------------------------------------------
-    K = args.steps
-    EV_EVERY = 4  # stage events on every 4th step: the five extra event records per step cost ~4 % of throughput
-    ev = [[L.gf_event_create() for _ in range(5)] for _ in range((K + EV_EVERY - 1) // EV_EVERY)]
-    ev_arr = [(ctypes.c_void_p * 5)(*e) for e in ev]
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    C.reset_launch_count()
+    # ---- device-resident timed regions -----------------------------------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # consecutive steps alternate between `--streams` CUDA streams so that the latency-bound FPS of scene
-    # i+1 (one 16-SM cluster) overlaps the propagation of scene i; every step still runs the whole hot path
-    nstreams = max(1, min(args.streams, S))
-    side = [torch.cuda.Stream(device=dev) for _ in range(nstreams)] if nstreams > 1 else [stream]
-    e0.record(stream)
-    for st_ in side:
-        if st_ is not stream:
+
+    def region():
+        barrier()
+        e0.record(stream)
+        for st_ in side:
             st_.wait_event(e0)
-    t_host0 = time.perf_counter()
-    for i in range(K):
-        if i % EV_EVERY == 0:
-            L.gf_set_stage_events(ev_arr[i // EV_EVERY], 5)
-        runners[i % S].run(xs[i % S], side[i % nstreams])
-    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host0) / K
-    for st_ in side:
-        if st_ is not stream:
+        t_host0 = time.perf_counter()
+        for c in range(calls):
+            launch(c)
+        host_ms = 1e3 * (time.perf_counter() - t_host0)
+        for st_ in side:
             done = torch.cuda.Event()
             done.record(st_)
             stream.wait_event(done)
-    e1.record(stream)
-    barrier()
-    launches = C.launch_count()
-    clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms_total], device=dev)
+        e1.record(stream)
+        barrier()
+        prop = [r.propagation_ms() for r in runners] if batched else []
+        return e0.elapsed_time(e1), host_ms, [p for p in prop if p]
+
+    probe_ms, _, _ = region()  # untimed: sizes the number of repetitions
+    R = args.repeats if args.repeats > 0 else int(max(5, min(21, 60.0 / max(probe_ms, 0.05))))
+    if dist is not None:  # the same count on every rank
+        t = torch.tensor([R], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        R = int(t.item())
+    sampler = ClockSampler(local)
+    sampler.start()
+    reps, host_reps, prop_in_region = [], [], []
+    for _ in range(R):
+        ms, host_ms, prop = region()
+        reps.append(ms)
+        host_reps.append(host_ms)
+        prop_in_region += prop
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor(reps, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # per repetition: the slowest rank
+        reps = [float(v) for v in t.tolist()]
+    ms_total = statistics.median(reps)
     ms_step = ms_total / K
     value = world * K * Q / (ms_total * 1e-3)
+    spread = (max(reps) - min(reps)) / ms_total
 
-    def stage(a, b):
-        v = [L.gf_event_elapsed_ms(e[a], e[b]) for e in ev]
-        v = [x for x in v if x >= 0]
-        return statistics.mean(v) if v else None
-
-    stage_ms = {"knn_grid_build": stage(0, 1), "knn_query_and_fps_join": stage(1, 2), "geodesic_pack_edges": stage(2, 3),
-                "geodesic_propagation": stage(3, 4), "whole_call": stage(0, 4)}
-    for e in ev:
-        for h in e:
-            L.gf_event_destroy(h)
-
-    # ---- short serial pass (one scene in flight): per-stage times without inter-scene overlap ----------
-    Ks = 12
-    ev_s = [[L.gf_event_create() for _ in range(5)] for _ in range(Ks)]
-    arr_s = [(ctypes.c_void_p * 5)(*e) for e in ev_s]
-    torch.cuda.synchronize(dev)
-    for i in range(Ks):
-        L.gf_set_stage_events(arr_s[i], 5)
-        runners[i % S].run(xs[i % S], stream)
-    torch.cuda.synchronize(dev)
-
-    def stage_serial(a, b):
-        v = [L.gf_event_elapsed_ms(e[a], e[b]) for e in ev_s[2:]]
-        v = [x for x in v if x >= 0]
-        return statistics.mean(v) if v else None
-
-    stage_ms_serial = {"knn_grid_build": stage_serial(0, 1), "knn_query_and_fps_join": stage_serial(1, 2),
-                       "geodesic_pack_edges": stage_serial(2, 3), "geodesic_propagation": stage_serial(3, 4),
-                       "whole_call": stage_serial(0, 4)}
-    for e in ev_s:
-        for h in e:
-            L.gf_event_destroy(h)
-
-    # ---- roofline of the level kernel -------------------------------------------------------------
-    Kn = k - 1
-    R = statistics.mean(reach) if reach else 0
-    b_geo = 4.0 * Q * N + (R + Q) * Kn * 12.0 + 4.0 * R  # per reached pair 12K+4 B, + dense output
-    peak, peak_src = measured_peak()
-    t_lv = stage_ms["geodesic_propagation"]
-    t_alone = stage_ms_serial["geodesic_propagation"]
-    achieved = (b_geo / (t_lv * 1e-3)) / 1e9 if t_lv else None
-    achieved_alone = (b_geo / (t_alone * 1e-3)) / 1e9 if t_alone else None
-    roofline = {"bound": "hbm", "kernel": "geo_seed_bfs_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": b_geo, "reached_pairs_R": R, "levels": max(levels) if levels else None,
-                "kernel_ms": t_lv, "kernel_ms_alone": t_alone, "achieved_alone": achieved_alone,
-                "frac_alone": (achieved_alone / peak) if achieved_alone else None,
-                "note": "kernel_ms is measured inside the timed region, where %d scenes are in flight and the kernel "
-                        "shares the SMs with the next scenes' FPS / kNN kernels; *_alone = serial pass" % nstreams,
-                "compulsory_bytes": 12.0 * N + 8.0 * N * k + 4.0 * Q * N}
-
-    # traffic was captured for c2 at 32 levels only
-    if not (args.workload == "c2" and cfg["max_step"] == 32):
-        roofline["traffic"] = None
-
-    # ---- the reference's evaluation setting (max_step = 256, geoformer_fs.py:502; SURVEY 8: "additionally
-    #      report max_step=256"): same scene, serial pass, propagation kernel only ---------------------------
-    eval_setting = None
-    if args.workload == "c2" and cfg["max_step"] == 32 and world == 1:
-        try:
-            r256 = GuidanceRunner(N, Q, k, cfg["radius"], 256, device=dev)
-            Ke = 6
-            ev_e = [[L.gf_event_create() for _ in range(5)] for _ in range(Ke)]
-            arr_e = [(ctypes.c_void_p * 5)(*e) for e in ev_e]
-            for i in range(Ke):
-                L.gf_set_stage_events(arr_e[i], 5)
-                r256.run(xs[i % S], stream)
+    # ---- one batch alone (nothing else on the GPU): the propagation launch and the whole call ------------------
+    alone = {}
+    if batched:
+        r0 = runners[0]
+        ts, ps = [], []
+        for _ in range(6):
             torch.cuda.synchronize(dev)
-            v = [L.gf_event_elapsed_ms(e[3], e[4]) for e in ev_e[2:]]
-            w = [L.gf_event_elapsed_ms(e[0], e[4]) for e in ev_e[2:]]
-            for e in ev_e:
-                for h in e:
-                    L.gf_event_destroy(h)
-            R256 = int(r256.stats[0].item())
-            b256 = 4.0 * Q * N + (R256 + Q) * Kn * 12.0 + 4.0 * R256
-            t256 = statistics.mean(v)
-            eval_setting = {"max_step": 256, "levels_run": int(r256.stats[1].item()), "reached_pairs_R": R256,
-                            "propagation_ms_alone": t256, "whole_call_ms_alone": statistics.mean(w),
-                            "maps_per_s_alone": Q / (statistics.mean(w) * 1e-3),
-                            "algorithmic_bytes_per_launch": b256, "achieved_alone": b256 / (t256 * 1e-3) / 1e9,
-                            "frac_alone": b256 / (t256 * 1e-3) / 1e9 / peak}
-            del r256
-        except Exception as ex:
-            eval_setting = {"error": repr(ex)}
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(side[0])
+            r0.replay(side[0])
+            b_.record(side[0])
+            torch.cuda.synchronize(dev)
+            ts.append(a_.elapsed_time(b_))
+            ps.append(r0.propagation_ms())
+        alone = {"call_ms": statistics.median(ts[1:]), "propagation_ms": statistics.median(ps[1:]), "scenes": B}
 
-    # ---- the two distance -> bias epilogues, timed on their own ---------------------
-    epilogues = None
+    # ---- per-stage times of ONE scene alone (plain launches, stage events of the library) ---------------------
+    stage_ms_serial = None
     try:
-        from geoformer_b200.bias import decoder_relative_embedding, decoder_relative_pos, mask_head_relative_coords
-        from geoformer_b200.pointnet2 import _ext as p2
-
-        Cn = 2048  # contexts of the real model (geoformer_fs.py:630-645); the seeds are their prefix
-        ctx = p2.furthest_point_sampling(xs[0][None].contiguous(), Cn)
-        geo0 = runners[0].geo if S == 1 else runners[0].run(xs[0], stream)[1]
-        ctx_xyz = xs[0][ctx[0].long()][None].contiguous()
-        q_xyz = ctx_xyz[:, :Q].contiguous()
+        r1 = GuidanceRunner(N, Q, k, cfg["radius"], cfg["max_step"], device=dev)
+        Ks = 10
+        ev_s = [[L.gf_event_create() for _ in range(5)] for _ in range(Ks)]
+        arr_s = [(ctypes.c_void_p * 5)(*e) for e in ev_s]
+        for i in range(Ks):
+            L.gf_set_stage_events(arr_s[i], 5)
+            r1.run(xs[i % S], stream)
         torch.cuda.synchronize(dev)
 
-        def timeit(fn, reps=10):
-            fn()
-            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a_.record(stream)
-            for _ in range(reps):
-                fn()
-            b_.record(stream)
-            torch.cuda.synchronize(dev)
-            return a_.elapsed_time(b_) / reps
+        def stage_serial(a, b):
+            v = [L.gf_event_elapsed_ms(e[a], e[b]) for e in ev_s[3:]]
+            v = [x for x in v if x >= 0]
+            return statistics.median(v) if v else None
 
-        t_dec = timeit(lambda: decoder_relative_pos([geo0], ctx, q_xyz, ctx_xyz))
-        t_mask = timeit(lambda: mask_head_relative_coords(geo0, xs[0], q_xyz[0]))
-        rmax0 = geo0.max(dim=1).values.contiguous()  # = the runner's row_max by-product (tests/test_gpu_parity.py)
-        t_mask1 = timeit(lambda: mask_head_relative_coords(geo0, xs[0], q_xyz[0], row_max=rmax0))
-        gauss_B = torch.randn(3, 32, device=dev)  # d_pos = 64 (config dec_dim), pos_embedding.py:38-41
-        pc = [xs[0].min(0)[0][None].contiguous(), xs[0].max(0)[0][None].contiguous()]
-        t_four = timeit(lambda: decoder_relative_embedding([geo0], ctx, q_xyz, ctx_xyz, gauss_B, pc))
-        b_four = 4.0 * Q * Cn * (1 + 64)          # gather + (B,Q,C,64) write; the (B,Q,C,3) tensor never exists
-        b_dec = 4.0 * Q * Cn * (1 + 3)            # gather + (B,Q,C,3) write
-        b_mask = 4.0 * Q * N * (1 + 3) + 12.0 * N  # one read of geo + (Q,3,N) write + coords
-        epilogues = {
-            "decoder_bias": {"ms": t_dec, "algorithmic_bytes": b_dec, "GBps": b_dec / t_dec / 1e6},
-            "decoder_bias_fourier": {"ms": t_four, "algorithmic_bytes": b_four, "GBps": b_four / t_four / 1e6,
-                                     "frac_of_hbm_peak": b_four / t_four / 1e6 / peak,
-                                     "note": "geoformer_fs.py:680-712 fused: gather, fill, normalise, 3x32 projection, "
-                                             "sin|cos, written once as (B,Q,C,64)"},
-            "mask_head_bias": {"ms": t_mask, "algorithmic_bytes": b_mask, "GBps": b_mask / t_mask / 1e6,
-                               "frac_of_hbm_peak": b_mask / t_mask / 1e6 / peak,
-                               "note": "timed through the Python call incl. output allocation; the kernel reads geo "
-                                       "twice (row max, then the element-wise pass)"},
-            "mask_head_bias_with_row_max": {"ms": t_mask1, "algorithmic_bytes": b_mask, "GBps": b_mask / t_mask1 / 1e6,
-                                            "frac_of_hbm_peak": b_mask / t_mask1 / 1e6 / peak,
-                                            "note": "row maxima taken from the propagation kernel (gf_guidance row_max): "
-                                                    "geo is read once, traffic = algorithmic bytes"},
-        }
+        stage_ms_serial = {"knn_grid_build": stage_serial(0, 1), "knn_query_and_fps_join": stage_serial(1, 2),
+                           "geodesic_propagation": stage_serial(3, 4), "whole_call": stage_serial(0, 4)}
+        for e in ev_s:
+            for h in e:
+                L.gf_event_destroy(h)
+        del r1
     except Exception as ex:
-        epilogues = {"error": repr(ex)}
+        stage_ms_serial = {"error": repr(ex)}
+
+    # ---- roofline of the propagation launch ----------------------------------------------------------
+    Kn = k - 1
+    R_pairs = statistics.mean(reach) if reach else 0
+    b_geo = 4.0 * Q * N + (R_pairs + Q) * Kn * 12.0 + 4.0 * R_pairs  # per reached pair 12K+4 B, + dense output
+    peak, peak_src = measured_peak()
+    per_launch = b_geo * B
+    t_in = statistics.median(prop_in_region) if prop_in_region else None
+    t_alone = alone.get("propagation_ms") if alone else (stage_ms_serial or {}).get("geodesic_propagation")
+    if not batched:
+        t_in = t_in or t_alone
+    achieved = per_launch / (t_in * 1e-3) / 1e9 if t_in else None
+    achieved_alone = per_launch / (t_alone * 1e-3) / 1e9 if t_alone else None
+    traffic, traffic_date = ncu_traffic(args.workload, cfg["max_step"], B)
+    roofline = {"bound": "hbm", "kernel": "geo_bfs_batch_kernel" if batched else "geo_seed_bfs_kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": traffic, "traffic_captured": traffic_date, "peak_source": peak_src,
+                "scenes_per_launch": B, "algorithmic_bytes_per_launch": per_launch,
+                "algorithmic_bytes_per_scene": b_geo, "reached_pairs_R_per_scene": R_pairs,
+                "levels": max(levels) if levels else None,
+                "kernel_ms": t_in, "kernel_ms_samples": len(prop_in_region), "kernel_ms_alone": t_alone,
+                "achieved_alone": achieved_alone, "frac_alone": (achieved_alone / peak) if achieved_alone else None,
+                "note": "kernel_ms = duration of the propagation launch (one per batch of %d scenes) between two event "
+                        "nodes of the replayed graph, inside the timed regions, where the next batch's FPS / kNN "
+                        "kernels share the SMs; *_alone = the same launch with nothing else running" % B,
+                "compulsory_bytes_per_scene": 12.0 * N + 8.0 * N * k + 4.0 * Q * N}
+
+    extras = {}
+    if not args.no_extras and world == 1:
+        extras = extra_records(args, cfg, xs, dev, stream, peak)
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------
     e2e = None
@@ -595,13 +606,29 @@ def run_ours(args):
                "d2h_achieved_GBps": hgs[0].d2h_bytes * Ke / dt / 1e9,
                "d2h_bytes_per_step": hgs[0].d2h_bytes, "steps": Ke, "ms_per_step": 1e3 * dt / Ke,
                "call": "gf_guidance_host (pinned host buffers, %d overlapped host threads)" % nthreads}
+        del hgs
+
+    # ---- one large scene split by seed blocks over the ranks, multi-rank runs only --------
+    sharded = None
+    if dist is not None and args.workload == "c2":
+        try:
+            from geoformer_b200.scenes import CONFIGS
+
+            for r in runners:
+                if batched:
+                    r.close()
+            runners = []
+            torch.cuda.empty_cache()
+            sharded = seed_sharded_record(dict(CONFIGS["c4"]), "fused", 6, dist, dev, rank, world)
+        except Exception as ex:
+            sharded = {"error": repr(ex)}
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            port = CpuPort(cfg, budget_s=6.0)
-            ts = [port.step()[0] for _ in range(2)]
+            port = CpuPort(cfg)
+            ts = [port.step(i)[0] for i in range(3)]
             cpu = {"value": Q / min(ts), "unit": "maps/s", "cores": port.cores, "kind": "port", "sample": port.sample}
         except Exception as ex:  # the benchmark itself must not depend on the checker
             cpu = {"value": None, "unit": "maps/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
@@ -610,21 +637,117 @@ def run_ours(args):
         line = {
             "metric": "geodesic maps/sec", "value": value, "unit": "maps/s", "n_gpus": world, "steps": K,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_block(cfg, args, extra={
-                "parallelism": "scene-parallel x%d (one scene per rank per step, no collective; every rank runs the "
-                               "same %d scenes)" % (world, S),
-                "l2": "%d rotating scenes per rank, %.0f MB footprint each (> 126 MB L2 in total)" % (S, per_scene / 1e6),
-                "streams": nstreams}),
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "stage_ms": stage_ms, "stage_ms_serial": stage_ms_serial, "epilogues": epilogues,
-            "eval_setting_max_step_256": eval_setting, "scenes_per_s": value / Q,
-            "host_enqueue_ms_per_step": host_enqueue_ms, "host_cpus_bound_to_gpu_node": numa_cpus,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(cfg, args),
+            "parallelism": "scene-parallel x%d (one scene per rank per step, no collective; every rank runs the same "
+                           "%d scenes)" % (world, S),
+            "pipeline": {"scenes_per_call": B, "calls_per_region": calls, "calls_in_flight": n_run,
+                         "cuda_graph_replay": bool(batched and not args.no_graph), "kernels_per_call": launches_per_call},
+            "repeats_ms": reps, "repeats": R, "repeat_spread": spread,
+            "e2e": e2e, "gpu_launches": calls * (launches_per_call or 0), "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "one_batch_alone": alone, "stage_ms_serial": stage_ms_serial,
+            "scenes_per_s": value / Q, "host_enqueue_ms_per_step": statistics.median(host_reps) / K,
+            "host_cpus_bound_to_gpu_node": numa_cpus, "seed_sharded_c4": sharded,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def extra_records(args, cfg, xs, dev, stream, peak):
+    """N=1 only, all outside the timed regions: the reference's evaluation and model settings, the two epilogues."""
+    import torch
+
+    from geoformer_b200 import _capi as C
+    from geoformer_b200.guidance import BatchGuidanceRunner, GuidanceRunner
+
+    L = C.lib()
+    N, Q, k = cfg["n"], cfg["Q"], cfg["k"]
+    S = len(xs)
+    out = {}
+
+    def batch_alone(kk, radius, max_step, B):
+        r = BatchGuidanceRunner(N, B, Q, kk, radius, max_step, device=dev, stage_events=True)
+        r.load([xs[b % S] for b in range(B)])
+        ts, ps = [], []
+        for _ in range(5):
+            torch.cuda.synchronize(dev)
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(stream)
+            r.replay(stream)
+            b_.record(stream)
+            torch.cuda.synchronize(dev)
+            ts.append(a_.elapsed_time(b_))
+            ps.append(r.propagation_ms())
+        reached = float(r.stats[:, 0].double().mean().item())
+        lev = int(r.stats[:, 1].max().item())
+        r.close()
+        return statistics.median(ts[1:]), statistics.median(ps[1:]), reached, lev
+
+    # ---- the reference's evaluation setting (max_step = 256, geoformer_fs.py:502; SURVEY 8: "additionally
+    #      report max_step=256") and the model's own call (neighbor=64, radius=0.05, max_step=256, :497-506) -------
+    if args.workload == "c2" and cfg["max_step"] == 32:
+        for name, kk, rad, ms in (("eval_setting_max_step_256", k, cfg["radius"], 256),
+                                  ("model_setting_k64_r005_ms256", 64, 0.05, 256)):
+            try:
+                B = 4
+                call, prop, reached, lev = batch_alone(kk, rad, ms, B)
+                b_s = 4.0 * Q * N + (reached + Q) * (kk - 1) * 12.0 + 4.0 * reached
+                out[name] = {"neighbor": kk, "radius": rad, "max_step": ms, "scenes_per_call": B, "levels_run": lev,
+                             "reached_pairs_R_per_scene": reached, "call_ms_per_scene_alone": call / B,
+                             "propagation_ms_per_scene_alone": prop / B, "maps_per_s_alone": Q * B / (call * 1e-3),
+                             "algorithmic_bytes_per_scene": b_s, "achieved_alone": b_s * B / (prop * 1e-3) / 1e9,
+                             "frac_alone": b_s * B / (prop * 1e-3) / 1e9 / peak}
+            except Exception as ex:
+                out[name] = {"error": repr(ex)}
+
+    # ---- the two distance -> bias epilogues (SURVEY a10 / a11), timed on their own ---------------------
+    try:
+        from geoformer_b200.bias import decoder_relative_embedding, decoder_relative_pos, mask_head_relative_coords
+        from geoformer_b200.pointnet2 import _ext as p2
+
+        Cn = 2048  # contexts of the real model (geoformer_fs.py:630-645); the seeds are their prefix
+        ctx = p2.furthest_point_sampling(xs[0][None].contiguous(), Cn)
+        r1 = GuidanceRunner(N, Q, k, cfg["radius"], cfg["max_step"], device=dev)
+        geo0 = r1.run(xs[0], stream)[1]
+        ctx_xyz = xs[0][ctx[0].long()][None].contiguous()
+        q_xyz = ctx_xyz[:, :Q].contiguous()
+        torch.cuda.synchronize(dev)
+
+        def timeit(fn, reps=10):
+            fn()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(stream)
+            for _ in range(reps):
+                fn()
+            b_.record(stream)
+            torch.cuda.synchronize(dev)
+            return a_.elapsed_time(b_) / reps
+
+        t_dec = timeit(lambda: decoder_relative_pos([geo0], ctx, q_xyz, ctx_xyz))
+        t_mask = timeit(lambda: mask_head_relative_coords(geo0, xs[0], q_xyz[0]))
+        rmax0 = r1.row_max.clone()
+        t_mask1 = timeit(lambda: mask_head_relative_coords(geo0, xs[0], q_xyz[0], row_max=rmax0))
+        gauss_B = torch.randn(3, 32, device=dev)  # d_pos = 64 (config dec_dim), pos_embedding.py:38-41
+        pc = [xs[0].min(0)[0][None].contiguous(), xs[0].max(0)[0][None].contiguous()]
+        t_four = timeit(lambda: decoder_relative_embedding([geo0], ctx, q_xyz, ctx_xyz, gauss_B, pc))
+        b_four = 4.0 * Q * Cn * (1 + 64)          # gather + (B,Q,C,64) write; the (B,Q,C,3) tensor never exists
+        b_dec = 4.0 * Q * Cn * (1 + 3)            # SURVEY 8(d): gather + (B,Q,C,3) write
+        b_mask = 4.0 * Q * N * (1 + 3) + 12.0 * N  # one read of geo + (Q,3,N) write + coords
+        out["epilogues"] = {
+            "decoder_bias": {"ms": t_dec, "algorithmic_bytes": b_dec, "GBps": b_dec / t_dec / 1e6},
+            "decoder_bias_fourier": {"ms": t_four, "algorithmic_bytes": b_four, "GBps": b_four / t_four / 1e6,
+                                     "frac_of_hbm_peak": b_four / t_four / 1e6 / peak},
+            "mask_head_bias": {"ms": t_mask, "algorithmic_bytes": b_mask, "GBps": b_mask / t_mask / 1e6,
+                               "frac_of_hbm_peak": b_mask / t_mask / 1e6 / peak},
+            "mask_head_bias_with_row_max": {"ms": t_mask1, "algorithmic_bytes": b_mask, "GBps": b_mask / t_mask1 / 1e6,
+                                            "frac_of_hbm_peak": b_mask / t_mask1 / 1e6 / peak},
+        }
+        del r1
+    except Exception as ex:
+        out["epilogues"] = {"error": repr(ex)}
+    return out
 
 
 if __name__ == "__main__":

@@ -421,26 +421,38 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
   }
 }
 
-// ---- the batched two-bitmap kernel (scenes whose bitmaps fit on chip: N <~ 860k) -----------------------------
-// Same algorithm and per-seed state as geo_seed_bfs_kernel<2, .>, restated for THROUGHPUT:
-//  * A per-seed run is a chain of dependent latencies (per level: queue -> edge row (L2) -> visited words ->
-//    barrier -> bitmap scan -> counter atomic -> queue, plus three dependent global loads per won point), measured
-//    at 3.5 us per level for a 15-point frontier and 8 us for 800 points with two 1024-thread CTAs per SM -- the SM
-//    issues at ~40 % while its 2048 thread slots are full.  So the work items are (scene, seed) pairs of a whole
-//    BATCH of scenes (the reference's own call is batched: cal_geodesic_vectorize loops over the scenes of a batch,
-//    geodesic_utils.py:98), pulled from one counter by persistent CTAs of 256 / 512 threads, 7 / 4 per SM: three to
-//    four times as many chains in flight per SM, one launch, one tail per batch instead of one per scene.
-//  * Edge targets are stored ENCODED (geo_enc_target) so that the visited test is four instructions.
-//  * The distance of a point won at level L-1 needs three dependent loads (its key, then the edge length and the
-//    parent's distance).  The key load of a thread's first point is issued when level L starts and the other two
-//    after the claims, so the chain runs under the claims instead of after them.
+// ---- the batched kernel (scenes whose two bitmaps fit on chip: N <~ 860k) -------------------------------------
+// Same algorithm as geo_seed_bfs_kernel<2, .> (level-synchronous first-visit BFS per seed, RED.MIN claim keys that
+// reproduce the reference's tie rule, frontier read off a claimed bitmap), restated around what the round-2
+// profiles showed: a per-seed run is a CHAIN OF DEPENDENT MEMORY LATENCIES (per level: queue -> edge row ->
+// visited words -> barrier -> bitmap scan -> queue, plus the loads that turn a winning key into a distance), the
+// SM issues at ~40 % with all its thread slots taken, 30 % of the warp time is spent at the barrier behind the
+// slowest warp of a level, and that warp is slow because its loads miss L2: with the claims made in the seed's own
+// output row, 296 concurrently live rows of 4N bytes (118 MB at N = 100k) are filled with -1 and then hit at random.
+//  * CELL ORDER.  The propagation runs on the kNN grid's cell-order numbering of the points (rank / order of
+//    gf_knn.cu: points of a cell are consecutive, cells of a row adjacent), so a frontier -- a shell in space --
+//    touches a few dense runs of ids instead of N/8 random sectors.
+//  * CLAIMS AND DISTANCES IN PER-CTA SCRATCH, not in the output row: claim[t] (32-bit key, RED.MIN) and dist[t]
+//    are indexed by cell-order id, so a seed touches ~13 % of their sectors (its reach) and they stay in L2.  A
+//    claim entry is reset by the thread that resolves it, so the array is cleared once per CTA, not per seed.
+//  * THE OUTPUT ROW IS WRITTEN ONCE, streaming, after the seed's last level: out[i] = visited(rank[i]) ?
+//    dist[rank[i]] : -1 (geodesic_utils.py:113 fills with -1 first; same result).  No read-modify-write of the
+//    402 MB/s-per-scene matrix, DRAM traffic = the matrix itself.
+//  * The tie rule needs the ORIGINAL parent index (smallest parent index, then slot, wins): keys are
+//    order[p] << slot_bits | slot; resolving maps the winner back through rank[].
+//  * Work items are the (scene, seed) pairs of a whole BATCH of scenes (the reference's call is batched:
+//    cal_geodesic_vectorize loops over the scenes of a batch, geodesic_utils.py:98), pulled from one counter by
+//    persistent CTAs: one launch, one tail per batch instead of one per scene.
+//  * Edge targets are stored ENCODED (see geo_claim4_enc) so that the visited test is four instructions.
 constexpr int GEO_MAXB = 16;  // scenes per launch (descriptors travel in the kernel parameters)
+constexpr uint32_t GEO_UNCLAIMED = 0xFFFFFFFFu;
 
 struct GeoScene {
-  const int *tgt;             // (N + 1, KP) encoded edge targets
+  const int *tgt;             // (N + 1, KP) encoded edge targets, rows and targets in cell order
   const float *len;           // (N + 1, KP) edge lengths
-  const int *seeds;           // (Q)
-  float *geo;                 // (Q, N)
+  const int *rank, *order;    // cell-order position of an original index and back; both null = identity
+  const int *seeds;           // (Q) original indices
+  float *geo;                 // (Q, N), original order
   float *row_max;             // optional (Q)
   unsigned long long *stats;  // optional: [0] reached pairs, [1] deepest level (device)
   int N, Q, item0, bitmap_words;
@@ -448,8 +460,10 @@ struct GeoScene {
 struct GeoBatchArgs {
   GeoScene sc[GEO_MAXB];
   int B, total_items, max_step, slot_bits, qcap;
-  int *overflow;  // per CTA: ovf_stride frontier entries beyond the on-chip queue
-  size_t ovf_stride;
+  int *overflow;    // per CTA: ovf_stride frontier entries beyond the on-chip queue
+  uint32_t *claim;  // per CTA: arr_stride claim keys
+  float *dist;      // per CTA: arr_stride distances
+  size_t ovf_stride, arr_stride;
   unsigned *item_counter;
 #ifdef GF_TRACE
   long long *trace, *trace2;
@@ -459,10 +473,10 @@ struct GeoBatchArgs {
 // ENCODED edge targets: the edge table stores a target t as (t >> 5) << 7 | (t & 31), i.e. the byte offset of its
 // bitmap word shifted left by 5 with the bit number in the low five bits.  The visited test of an edge -- 93 % of
 // the edges of a kNN graph fail it -- is then four instructions (shift, LDS, funnel shift for the bit, LOP3 into a
-// predicate) instead of eight; the byte offset into the output row (4 * t) is only rebuilt on the rare hit.
+// predicate) instead of eight; the byte offset into the claim array (4 * t) is only rebuilt on the rare hit.
 // The four visited words are fetched first (independent loads), then tested.
 __device__ __forceinline__ void geo_claim4_enc(uint32_t key, const int4 t, uint32_t vis_s, uint32_t clm_s,
-                                               unsigned char *rowb) {
+                                               unsigned char *claimb) {
   const unsigned tt[4] = {(unsigned)t.x, (unsigned)t.y, (unsigned)t.z, (unsigned)t.w};
   uint32_t w[4];
 #pragma unroll
@@ -473,7 +487,7 @@ __device__ __forceinline__ void geo_claim4_enc(uint32_t key, const int4 t, uint3
     if (!(w[e] & bit)) {
       const uint32_t boff = (tt[e] & ~127u) | ((tt[e] & 31u) << 2);  // 4 * t
       // both fire and forget (RED.MIN, ATOMS.OR without a destination)
-      asm volatile("red.relaxed.gpu.global.min.u32 [%0], %1;" ::"l"(rowb + boff), "r"(key + e) : "memory");
+      asm volatile("red.relaxed.gpu.global.min.u32 [%0], %1;" ::"l"(claimb + boff), "r"(key + e) : "memory");
       asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(clm_s + (tt[e] >> 5)), "r"(bit) : "memory");
     }
   }
@@ -492,13 +506,22 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
   const unsigned tid = threadIdx.x;
   const unsigned lsb = sb - 2, sub = tid & ((1u << lsb) - 1u);
   const unsigned group = tid >> lsb, ngroups = THREADS >> lsb;
-  const uint32_t keybase = GEO_KEYBIT | (sub << 2);
+  const uint32_t keysub = sub << 2;
   int *ovf = a.overflow + (size_t)blockIdx.x * a.ovf_stride;
+  uint32_t *claim = a.claim + (size_t)blockIdx.x * a.arr_stride;
+  float *dist = a.dist + (size_t)blockIdx.x * a.arr_stride;
+  {  // all claim entries start unclaimed; afterwards every entry is reset by the thread that resolves it
+    uint4 *c4 = reinterpret_cast<uint4 *>(claim);
+    const uint4 ff = make_uint4(GEO_UNCLAIMED, GEO_UNCLAIMED, GEO_UNCLAIMED, GEO_UNCLAIMED);
+    for (size_t i = tid; i < a.arr_stride / 4; i += THREADS) c4[i] = ff;
+  }
   // opaque copies: without them ptxas re-derives these addresses (S2R of the CTA's shared window, constant-bank
   // loads, 64-bit multiply-adds) inside every claim instead of spending a register on them
   uint32_t vis_s = (uint32_t)__cvta_generic_to_shared(vis), fq_s = (uint32_t)__cvta_generic_to_shared(fq);
   asm volatile("mov.u32 %0, %0;" : "+r"(vis_s));
   asm volatile("mov.u32 %0, %0;" : "+r"(fq_s));
+  asm volatile("mov.u64 %0, %0;" : "+l"(claim));
+  unsigned char *claimb = reinterpret_cast<unsigned char *>(claim);
   auto fq_at = [&](int i) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(fq_s + 4u * (unsigned)i) : "memory");
@@ -514,6 +537,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
     while (b + 1 < a.B && a.sc[b + 1].item0 <= item) ++b;
     const GeoScene &S = a.sc[b];
     const int q = item - S.item0, N = S.N, words = S.bitmap_words;
+    const int *__restrict__ rank = S.rank, *__restrict__ order = S.order;
     // frontier entry i >= QC lives in the CTA's overflow area: consecutive levels hold disjoint point sets
     // (F_L + F_{L+1} <= N + 1), so one buffer of N + 2 entries serves both, odd levels from the bottom, even from the top
     auto ovf_at = [&](int i, int parity) { return parity ? (size_t)(i - QC) : (size_t)N + 1 - (size_t)(i - QC); };
@@ -522,29 +546,17 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
     uint32_t clm_s = vis_s + 4u * (uint32_t)words;
     asm volatile("mov.u32 %0, %0;" : "+r"(clm_s));
     const int4 *__restrict__ trow = reinterpret_cast<const int4 *>(S.tgt) + sub;  // + (p << lsb)
-    float *row = S.geo + (size_t)q * N;
-    asm volatile("mov.u64 %0, %0;" : "+l"(row));
-    uint32_t *rowu = reinterpret_cast<uint32_t *>(row);
-    unsigned char *rowb = reinterpret_cast<unsigned char *>(row);
 #ifdef GF_TRACE
     long long tr_t0 = 0, tr_t1 = 0;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0));
 #endif
-    {  // init: row = -1 (geodesic_utils.py:113), visited = claimed = {} (:114)
-      const size_t head = ((16 - ((uintptr_t)row & 15)) & 15) / 4;
-      const size_t h = head < (size_t)N ? head : (size_t)N;
-      const size_t nvec = ((size_t)N - h) / 4;
-      float4 *r4 = reinterpret_cast<float4 *>(row + h);
-      const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
-      for (size_t i = tid; i < nvec; i += THREADS) r4[i] = m1;
-      if ((size_t)tid < h) row[tid] = -1.f;
-      const size_t tail0 = h + nvec * 4;
-      if ((size_t)tid < (size_t)N - tail0) row[tail0 + tid] = -1.f;
+    {  // visited = claimed = {} (geodesic_utils.py:114)
       uint4 *b4 = reinterpret_cast<uint4 *>(vis);
       for (int i = tid; i < words / 2; i += THREADS) b4[i] = make_uint4(0u, 0u, 0u, 0u);  // vis, clm contiguous
     }
-    const int s = S.seeds[q];
-    const bool seed_ok = s >= 0 && s < N;  // the reference would raise an index error; the row stays -1
+    const int so = S.seeds[q];
+    const bool seed_ok = so >= 0 && so < N;  // the reference would raise an index error; the row stays -1
+    const int s = seed_ok ? (rank ? __ldg(rank + so) : so) : 0;
     __syncthreads();
     if (tid == 0) {
       s_next_n[0] = s_next_n[1] = 0;
@@ -557,15 +569,17 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
     // visited filter (:123), so a seed that appears in its own neighbour row is re-won at level 1.
     int level = 0;
     unsigned long long reached = 0;
-    float rmax = 0.f;  // largest distance this thread wrote into the row (all are >= 0)
-    // distance of a point won at level `won`: the key left in its row entry is the reference's winner.
+    float rmax = 0.f;  // largest distance of this seed seen by this thread (all are >= 0)
+    // distance of a point won at level `won`: the key left in its claim entry is the reference's winner.
     // level 1: the distance is the edge itself (:127); later: edge + parent's distance (:139,:144)
     auto resolve = [&](int t, int won) {
-      const uint32_t key = ld_cg_u32(rowu + t);
-      const unsigned p = (key & 0x7fffffffu) >> sb, j = key & (KP - 1);
+      const uint32_t key = ld_cg_u32(claim + t);
+      claim[t] = GEO_UNCLAIMED;
+      const unsigned po = key >> sb, j = key & (KP - 1);
+      const unsigned p = rank ? (unsigned)__ldg(rank + po) : po;
       const float w = __ldg(S.len + ((size_t)p << sb) + j);
-      const float d = won == 1 ? w : __fadd_rn(w, __uint_as_float(ld_cg_u32(rowu + p)));
-      row[t] = d;
+      const float d = won == 1 ? w : __fadd_rn(w, __ldcg(dist + p));
+      dist[t] = d;
       rmax = fmaxf(rmax, d);
     };
 #ifdef GF_TRACE
@@ -587,43 +601,49 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
       uint32_t rkey = 0;
       if (level > 1 && (int)tid < F) {
         rt = frontier((int)tid, (level - 1) & 1);
-        rkey = ld_cg_u32(rowu + rt);
+        rkey = ld_cg_u32(claim + rt);
       }
       // ---- claims: KP/4 lanes per frontier point; lanes past the end expand the sentinel point N -------------
       const int Fs = F < QC ? F : QC;
       for (int n0 = (int)group; n0 < Fs; n0 += (int)ngroups * U) {
-        unsigned pl[U];
+        unsigned pl[U], key[U];
         int4 t[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int at = n0 + u * (int)ngroups;
-          pl[u] = (unsigned)(at < Fs ? fq_at(at) : N) << lsb;
+          const int p = at < Fs ? fq_at(at) : N;
+          pl[u] = (unsigned)p << lsb;
+          key[u] = (unsigned)p;
+          if (order) key[u] = at < Fs ? (unsigned)__ldg(order + p) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) t[u] = __ldg(trow + pl[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (u > 0 && n0 + u * (int)ngroups >= Fs) continue;  // whole groups of sentinel lanes
-          geo_claim4_enc(keybase | (pl[u] << 2), t[u], vis_s, clm_s, rowb);
+          geo_claim4_enc((key[u] << sb) | keysub, t[u], vis_s, clm_s, claimb);
         }
       }
       for (int node = QC + (int)group; node < F; node += (int)ngroups) {  // spilled tail (rare)
-        const unsigned pl = (unsigned)ovf[ovf_at(node, (level - 1) & 1)] << lsb;
-        geo_claim4_enc(keybase | (pl << 2), __ldg(trow + pl), vis_s, clm_s, rowb);
+        const int p = ovf[ovf_at(node, (level - 1) & 1)];
+        const unsigned po = order ? (unsigned)__ldg(order + p) : (unsigned)p;
+        geo_claim4_enc((po << sb) | keysub, __ldg(trow + ((unsigned)p << lsb)), vis_s, clm_s, claimb);
       }
       GF_TR(1);
       // ---- the frontier's own distances (its points were won at level-1 and still hold their keys) ----------
       if (level > 1) {
         float rw = 0.f, rpd = 0.f;
-        if (rt >= 0) {  // second stage: both loads in flight while the rest of the frontier is resolved
-          const unsigned p = (rkey & 0x7fffffffu) >> sb, j = rkey & (KP - 1);
+        if (rt >= 0) {  // second stage: the loads below are in flight while the rest of the frontier is resolved
+          claim[rt] = GEO_UNCLAIMED;
+          const unsigned po = rkey >> sb, j = rkey & (KP - 1);
+          const unsigned p = rank ? (unsigned)__ldg(rank + po) : po;
           rw = __ldg(S.len + ((size_t)p << sb) + j);
-          if (level > 2) rpd = __uint_as_float(ld_cg_u32(rowu + p));
+          if (level > 2) rpd = __ldcg(dist + p);
         }
         for (int i = (int)tid + THREADS; i < F; i += THREADS) resolve(frontier(i, (level - 1) & 1), level - 1);
         if (rt >= 0) {
           const float d = level == 2 ? rw : __fadd_rn(rw, rpd);
-          row[rt] = d;
+          dist[rt] = d;
           rmax = fmaxf(rmax, d);
         }
       }
@@ -635,7 +655,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
       if (level == 1 && seed_ok && tid == (((unsigned)s >> 7) & (THREADS - 1))) {
         // the seed joins the visited set now; if no self edge re-won it, its distance stays 0
         // (a re-won seed holds its key until it is resolved with the other level-1 points)
-        if (ld_cg_u32(rowu + s) == GEO_UNVISITED) row[s] = 0.f;
+        if (ld_cg_u32(claim + s) == GEO_UNCLAIMED) dist[s] = 0.f;
         vis[(unsigned)s >> 5] |= 1u << (s & 31);
       }
       {
@@ -685,10 +705,33 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
     // the points won at the last executed level still hold their keys
     if (level >= 1)
       for (int i = tid; i < F; i += THREADS) resolve(frontier(i, level & 1), level);
-    if (level == 0 && seed_ok && tid == 0) row[s] = 0.f;  // max_step <= 0: only the seed entry (:118)
+    if (level == 0 && seed_ok && tid == 0) {  // max_step <= 0: only the seed entry (:118)
+      dist[s] = 0.f;
+      vis[(unsigned)s >> 5] |= 1u << (s & 31);
+    }
+    __syncthreads();  // every distance of the seed is in dist[], every reached point in the visited bitmap
+    {  // ---- the output row, written once: out[i] = visited(rank[i]) ? dist[rank[i]] : -1 (:113) ----------------
+      float *row = S.geo + (size_t)q * N;
+      auto value = [&](int r) {
+        uint32_t w;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(vis_s + (((unsigned)r >> 3) & ~3u)));
+        return (w >> (r & 31)) & 1u ? __ldcg(dist + r) : -1.f;
+      };
+      if ((((uintptr_t)row) & 15) == 0) {
+        const int nvec = N >> 2;
+        const int4 *__restrict__ rank4 = reinterpret_cast<const int4 *>(rank);
+        for (int i = tid; i < nvec; i += THREADS) {
+          const int4 r = rank ? __ldg(rank4 + i) : make_int4(4 * i, 4 * i + 1, 4 * i + 2, 4 * i + 3);
+          __stcs(reinterpret_cast<float4 *>(row) + i, make_float4(value(r.x), value(r.y), value(r.z), value(r.w)));
+        }
+        for (int i = nvec * 4 + (int)tid; i < N; i += THREADS) row[i] = value(rank ? __ldg(rank + i) : i);
+      } else {
+        for (int i = tid; i < N; i += THREADS) row[i] = value(rank ? __ldg(rank + i) : i);
+      }
+    }
     if (S.row_max) {
-      // max over the row = max over what was written (the seed's 0 included), or -1 for a row that stayed empty;
-      // distances are non-negative, so their bit patterns order like unsigned integers
+      // max over the row = max over the distances written (the seed's 0 included), or -1 for a row that stayed
+      // empty; distances are non-negative, so their bit patterns order like unsigned integers
       const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(rmax));
       if ((tid & 31u) == 0) s_rmax[tid >> 5] = wm;
       __syncthreads();
@@ -778,9 +821,11 @@ static void plan_geo(int N, int Q, GeoPlan *p) {
 // plan of the batched kernel
 struct GeoBatchPlan {
   int threads, unroll, per_sm, grid, qcap, words;
-  size_t smem, ovf_stride;
+  size_t smem, ovf_stride, arr_stride;
 };
-constexpr size_t GEO_OVF_BUDGET = (size_t)192 << 20;  // bytes of frontier overflow a launch may reserve
+// bytes of per-CTA scratch (frontier overflow + claim keys + distances: 12 bytes per point and CTA) a launch may
+// reserve before the number of CTAs is cut below what the SMs could hold (never below one per SM)
+constexpr size_t GEO_SCRATCH_BUDGET = (size_t)768 << 20;
 
 // true when the scene can run in the batched kernel (both bitmaps + a queue fit one CTA's shared memory)
 static bool geo_batchable(int maxN) {
@@ -816,8 +861,9 @@ static void plan_batch(int maxN, long long items, GeoBatchPlan *p) {
   p->qcap = best_q;
   p->smem = sizeof(int) * (size_t)best_q + 2 * sizeof(uint32_t) * (size_t)p->words;
   p->ovf_stride = (size_t)maxN + 2;
+  p->arr_stride = ((size_t)maxN + 1 + 3) & ~(size_t)3;  // claim keys / distances per CTA, whole 16-byte pieces
   long long grid = (long long)sms * best_fit;
-  const long long ovf_cap = (long long)(GEO_OVF_BUDGET / (sizeof(int) * p->ovf_stride));
+  const long long ovf_cap = (long long)(GEO_SCRATCH_BUDGET / (sizeof(int) * (p->ovf_stride + 2 * p->arr_stride)));
   if (grid > ovf_cap) grid = ovf_cap > sms ? ovf_cap : sms;
   if (grid > items) grid = items;
   p->grid = (int)(grid < 1 ? 1 : grid);
@@ -831,17 +877,21 @@ static size_t geo_edge_bytes(int N, int k) {
 size_t geodesic_batch_scratch_bytes(int maxN, long long items) {
   GeoBatchPlan p;
   plan_batch(maxN, items, &p);
-  return align256(sizeof(int) * p.ovf_stride * (size_t)p.grid) + align256(256) + 512;
+  return align256(sizeof(int) * p.ovf_stride * (size_t)p.grid) + 2 * align256(sizeof(int) * p.arr_stride * (size_t)p.grid) +
+         align256(256) + 1024;
 }
 
 size_t geodesic_workspace_bytes(int N, int k, int Q) {
-  size_t b = geo_edge_bytes(N, k);  // packed edge targets + lengths (+ sentinel row)
-  if (geo_batchable(N)) return b + geodesic_batch_scratch_bytes(N, Q) + 1024;
+  const size_t edges = geo_edge_bytes(N, k);  // packed edge targets + lengths (+ sentinel row)
   GeoPlan pl;
   plan_geo(N, Q, &pl);
-  b += align256(sizeof(int) * ((size_t)N + 2) * (size_t)pl.grid);  // frontier overflow
-  b += align256(256);                                              // seed counter + stats
-  return b + 1024;
+  // the per-scene kernel (big scenes; seed-sharded scenes of any size): frontier overflow, seed counter + stats
+  size_t rest = align256(sizeof(int) * ((size_t)N + 2) * (size_t)pl.grid) + align256(256);
+  if (geo_batchable(N)) {
+    const size_t r2 = geodesic_batch_scratch_bytes(N, Q);
+    rest = r2 > rest ? r2 : rest;
+  }
+  return edges + rest + 1024;
 }
 
 // workspace carve-up of the single-scene entry points, identical for sizing, packing and launching
@@ -946,13 +996,17 @@ int geodesic_batch_launch(const GeoSceneDesc *scenes, int B, int k, int max_step
   const int slot_bits = geo_slot_bits(k);
   for (int b = 0; b < B; ++b) {
     const GeoSceneDesc &d = scenes[b];
-    if ((((unsigned long long)d.N + 1) << slot_bits) >= GEO_KEYMAX) {
-      set_error("geodesic: N=%d with k=%d does not fit the 30-bit claim key (N << %d must be < 2^30)", d.N, k,
-                slot_bits);
+    if ((((unsigned long long)d.N + 1) << slot_bits) >= 0xFFFFFFFFull) {
+      set_error("geodesic: N=%d with k=%d does not fit the 32-bit claim key", d.N, k);
       return GF_ERR_INVALID;
     }
     GeoScene &s = ga.sc[b];
     s.tgt = d.tgt, s.len = d.len, s.seeds = d.seeds, s.geo = d.geo, s.row_max = d.row_max;
+    s.rank = d.rank, s.order = d.order;
+    if ((d.rank == nullptr) != (d.order == nullptr)) {
+      set_error("geodesic: scene %d: rank and order must be given together", b);
+      return GF_ERR_INVALID;
+    }
     s.stats = (unsigned long long *)d.stats;
     s.N = d.N, s.Q = d.Q, s.item0 = (int)items, s.bitmap_words = geo_bitmap_words(d.N);
     items += d.Q;
@@ -967,13 +1021,15 @@ int geodesic_batch_launch(const GeoSceneDesc *scenes, int B, int k, int max_step
   plan_batch(maxN, items, &p);
   Arena a(scratch, scratch_bytes);
   ga.overflow = a.take<int>(p.ovf_stride * (size_t)p.grid);
+  ga.claim = a.take<uint32_t>(p.arr_stride * (size_t)p.grid);
+  ga.dist = a.take<float>(p.arr_stride * (size_t)p.grid);
   ga.item_counter = a.take<unsigned>(64);
   if (!a.ok) {
     set_error("geodesic: scratch too small (%zu bytes given, %zu needed)", scratch_bytes,
               geodesic_batch_scratch_bytes(maxN, items));
     return GF_ERR_WORKSPACE;
   }
-  ga.ovf_stride = p.ovf_stride;
+  ga.ovf_stride = p.ovf_stride, ga.arr_stride = p.arr_stride;
   ga.B = B, ga.total_items = (int)items, ga.max_step = max_step, ga.slot_bits = slot_bits, ga.qcap = p.qcap;
   GF_CUDA(cudaMemsetAsync(ga.item_counter, 0, 256, st));
 #ifdef GF_TRACE
@@ -1016,7 +1072,8 @@ int geodesic_batch_launch(const GeoSceneDesc *scenes, int B, int k, int max_step
 // the fused hot path, gf_knn.cu TopK::store_edges, in the format geodesic_edge_buffers reported) -- no packing pass.
 int geodesic_run(const float *D, const void *I, int is64, int N, int k, const int *seeds, int Q, float radius,
                  int max_step, float *geo, int64_t *stats_out, void *workspace, size_t workspace_bytes,
-                 cudaStream_t st, float *const *peer_rows, int n_peers, float *row_max) {
+                 cudaStream_t st, float *const *peer_rows, int n_peers, float *row_max, const int *rank,
+                 const int *order) {
   if (n_peers < 0 || n_peers > GEO_MAX_PEERS || (n_peers > 0 && !peer_rows)) {
     set_error("geodesic: %d peers given, at most %d supported", n_peers, GEO_MAX_PEERS);
     return GF_ERR_INVALID;
@@ -1033,7 +1090,8 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
               geodesic_workspace_bytes(N, k, Q));
     return GF_ERR_WORKSPACE;
   }
-  const bool batched = geo_batchable(N);  // also the format of an already packed edge table
+  // also the format of an already packed edge table (seed-sharded scenes always run the per-scene kernel)
+  const bool batched = geo_batchable(N) && n_peers == 0;
   if (D != nullptr) {
     const long long total = ((long long)N + 1) << slot_bits;
     long long blocks = (total + 255) / 256;
@@ -1045,26 +1103,25 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
       geo_pack_edges_kernel<false><<<grid, 256, 0, st>>>(D, I, N, k, radius, slot_bits, batched ? 1 : 0, b.tgt, b.len);
     GF_LAUNCHED();
   }
-  if (batched && n_peers == 0) {
+  if (batched) {
     // stats of the batched kernel are accumulated with atomics: clear them here (16 bytes of the control block)
     Arena a(b.rest, b.rest_bytes);
     GeoBatchPlan p;
     plan_batch(N, Q, &p);
     (void)a.take<int>(p.ovf_stride * (size_t)p.grid);
+    (void)a.take<uint32_t>(p.arr_stride * (size_t)p.grid);
+    (void)a.take<float>(p.arr_stride * (size_t)p.grid);
     unsigned *ctl = a.take<unsigned>(64);
     unsigned long long *stats = (unsigned long long *)(ctl + 32);  // second half of the 256-byte control block
     GeoSceneDesc d;
     d.tgt = b.tgt, d.len = b.len, d.seeds = seeds, d.geo = geo, d.row_max = row_max;
+    d.rank = D == nullptr ? rank : nullptr, d.order = D == nullptr ? order : nullptr;  // a packed foreign graph: identity
     d.stats = stats_out ? (int64_t *)stats : nullptr;
     d.N = N, d.Q = Q;
     int rc = geodesic_batch_launch(&d, 1, k, max_step, b.rest, b.rest_bytes, st);  // its memset clears the stats too
     if (rc) return rc;
     if (stats_out) GF_CUDA(cudaMemcpyAsync(stats_out, stats, 16, cudaMemcpyDeviceToDevice, st));
     return GF_OK;
-  }
-  if (batched) {
-    set_error("geodesic: seed-sharded scenes use the plain edge format (internal error)");
-    return GF_ERR_INVALID;
   }
   GeoPlan p;
   plan_geo(N, Q, &p);

@@ -7,12 +7,14 @@ namespace gf {
 size_t geodesic_workspace_bytes(int N, int k, int Q);
 int geodesic_run(const float *D, const void *I, int is64, int N, int k, const int *seeds, int Q, float radius,
                  int max_step, float *geo, int64_t *stats_out, void *workspace, size_t workspace_bytes,
-                 cudaStream_t st, float *const *peer_rows = nullptr, int n_peers = 0, float *row_max = nullptr);
+                 cudaStream_t st, float *const *peer_rows = nullptr, int n_peers = 0, float *row_max = nullptr,
+                 const int *rank = nullptr, const int *order = nullptr);
 
 // ---- batched launch: the (scene, seed) pairs of several scenes in ONE kernel ----------------------------------
 struct GeoSceneDesc {
   const int *tgt;    // packed edge table of the scene, in the format geodesic_edge_buffers reported (encoded)
   const float *len;
+  const int *rank, *order;  // the numbering the table is written in (gf_knn.cuh: cell order); both null = original
   const int *seeds;  // (Q) device
   float *geo;        // (Q, N) device
   float *row_max;    // optional (Q)

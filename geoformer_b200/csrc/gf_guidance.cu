@@ -137,15 +137,18 @@ static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, in
   // arrays are only written when the caller asked for them
   KnnEdgeOut eo;
   eo.radius = radius;
-  rc = geodesic_edge_buffers(ws_geo, p.geo, N, k, Q, &eo.tgt, &eo.len, &eo.slot_bits, &eo.enc);
+  int enc = 0;
+  rc = geodesic_edge_buffers(ws_geo, p.geo, N, k, Q, &eo.tgt, &eo.len, &eo.slot_bits, &enc);
   if (rc) return rc;
+  if (n_peers > 0) enc = 0;  // seed-sharded scenes run the per-scene kernel: original numbering, plain targets
+  eo.rank = enc ? gb.rank : nullptr;
   rc = knn_grid_query(gb, nullptr, N, k, /*sqrt=*/1, knn_dist, nullptr, knn_idx32, st, &eo);
   if (rc) return rc;
   // join, then propagate
   if (!seeds_given) GF_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   stage_mark(ST_KNN_DONE, st);
   return geodesic_run(nullptr, nullptr, /*is64=*/0, N, k, seeds, Q, radius, max_step, geo, stats, ws_geo, p.geo, st,
-                      peer_geo, n_peers, row_max);
+                      peer_geo, n_peers, row_max, enc ? gb.rank : nullptr, enc ? gb.order : nullptr);
 }
 
 extern "C" int gf_guidance(const float *xyz, int N, int Q, int k, float radius, int max_step, int *seeds, float *geo,
@@ -261,12 +264,15 @@ extern "C" int gf_guidance_batch(const float *const *xyz, const int *Ns, int B, 
     if (rc) return rc;
     KnnEdgeOut eo;
     eo.radius = radius;
+    int enc = 0;
     rc = geodesic_edge_buffers(w + p.per_scene[b * 3 + 2], edge_b[b], Ns[b], k, 1, &eo.tgt, &eo.len, &eo.slot_bits,
-                               &eo.enc);
+                               &enc);
     if (rc) return rc;
+    eo.rank = gb.rank;  // cell-order table (every scene of a batched call is batchable: checked above)
     rc = knn_grid_query(gb, nullptr, Ns[b], k, /*sqrt=*/1, nullptr, nullptr, nullptr, ks, &eo);
     if (rc) return rc;
     desc[b].tgt = eo.tgt, desc[b].len = eo.len, desc[b].seeds = seeds[b], desc[b].geo = geo[b];
+    desc[b].rank = gb.rank, desc[b].order = gb.order;
     desc[b].row_max = row_max ? row_max[b] : nullptr;
     desc[b].stats = d_stats ? d_stats + 2 * b : nullptr;
     desc[b].N = Ns[b], desc[b].Q = Q;

@@ -245,11 +245,13 @@ __global__ void __launch_bounds__(256) knn_scan_kernel(KnnCtl *ctl, const int *_
 // build kernel 5: the points in cell order, each with its original index
 __global__ void knn_scatter_kernel(const float *__restrict__ xyz, int N, const int *__restrict__ cell_id,
                                    const int *__restrict__ slot_in_cell, const int *__restrict__ start,
-                                   float4 *__restrict__ sorted) {
+                                   float4 *__restrict__ sorted, int *__restrict__ order, int *__restrict__ rank) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     int pos = start[cell_id[i]] + slot_in_cell[i];
     float x = __ldg(xyz + (size_t)i * 3), y = __ldg(xyz + (size_t)i * 3 + 1), z = __ldg(xyz + (size_t)i * 3 + 2);
     sorted[pos] = make_float4(x, y, z, __int_as_float(i));
+    order[pos] = i;  // order[cell-order position] = original index
+    rank[i] = pos;   // rank[original index] = cell-order position
   }
 }
 
@@ -281,11 +283,17 @@ struct TopK {
   // The row of the propagation's edge table (gf_geodesic.cu: geo_pack_edges_kernel, same rule): neighbour
   // 1 + e of the result as edge e if it may ever be used (sqrt(d2) <= radius, geodesic_utils.py:123,151),
   // else an edge to the sentinel point N; padded with such edges to KP = 1 << slot_bits entries.
-  __device__ __forceinline__ void store_edges(int k, float radius, int N, int slot_bits, int enc,
+  // rank != nullptr: the table lives in CELL ORDER (the caller passes the row of the query's cell-order position and
+  // targets are translated through rank[]) with encoded targets; else original indices, plain.
+  __device__ __forceinline__ void store_edges(int k, float radius, int N, int slot_bits, const int *__restrict__ rank,
                                               int *__restrict__ tgt, float *__restrict__ len) const {
     const int KP = 1 << slot_bits;
-    auto code = [&](int t) { return enc ? (int)((((unsigned)t >> 5) << 7) | ((unsigned)t & 31u)) : t; };
-    const int none = code(N);
+    auto code = [&](int t) {
+      if (!rank) return t;
+      const unsigned r = (unsigned)__ldg(rank + t);
+      return (int)(((r >> 5) << 7) | (r & 31u));
+    };
+    const int none = rank ? (int)((((unsigned)N >> 5) << 7) | ((unsigned)N & 31u)) : N;
     if (k == KT && KP == KT) {  // the usual case (k a power of two): whole 16-byte stores
 #pragma unroll
       for (int e0 = 0; e0 < KT; e0 += 4) {
@@ -348,7 +356,7 @@ __global__ void __launch_bounds__(128)
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nq) return;
   if (eo.tgt && s == 0) {  // the sentinel row N: only edges to N
-    const int none = eo.enc ? (int)((((unsigned)nq >> 5) << 7) | ((unsigned)nq & 31u)) : nq;
+    const int none = eo.rank ? (int)((((unsigned)nq >> 5) << 7) | ((unsigned)nq & 31u)) : nq;
     for (int e = 0; e < (1 << eo.slot_bits); ++e)
       eo.tgt[((size_t)nq << eo.slot_bits) + e] = none, eo.len[((size_t)nq << eo.slot_bits) + e] = 0.f;
   }
@@ -423,9 +431,10 @@ __global__ void __launch_bounds__(128)
   if (dist || idx64 || idx32)
     top.store(k, do_sqrt != 0, dist ? dist + (size_t)row * k : nullptr, idx64 ? idx64 + (size_t)row * k : nullptr,
               idx32 ? idx32 + (size_t)row * k : nullptr);
-  if (eo.tgt)  // self query only (nq == N): the propagation's edge rows, written straight from the registers
-    top.store_edges(k, eo.radius, nq, eo.slot_bits, eo.enc, eo.tgt + ((size_t)row << eo.slot_bits),
-                    eo.len + ((size_t)row << eo.slot_bits));
+  if (eo.tgt) {  // self query only (nq == N): the propagation's edge rows, written straight from the registers
+    const size_t er = (size_t)(eo.rank ? s : row) << eo.slot_bits;  // cell-order row (= this thread) or original row
+    top.store_edges(k, eo.radius, nq, eo.slot_bits, eo.rank, eo.tgt + er, eo.len + er);
+  }
 }
 
 // ---- brute force (algo 1) -----------------------------------------------------------------------
@@ -481,7 +490,7 @@ size_t knn_grid_workspace_bytes(int N) {
   b += align256(sizeof(KnnCtl));
   b += align256(sizeof(int) * (size_t)knn_cap_coarse(N));
   b += align256(sizeof(int) * (size_t)(knn_cap_fine(N) + 4)) * 2;  // cell_count, cell_start
-  b += align256(sizeof(int) * (size_t)N) * 2;                        // cell_id, slot_in_cell
+  b += align256(sizeof(int) * (size_t)N) * 4;                        // cell_id, slot_in_cell, order, rank
   b += align256(sizeof(float4) * (size_t)N);
   return b + 1024;
 }
@@ -512,6 +521,8 @@ int knn_grid_build(const float *xyz, int N, int k, void *workspace, size_t works
   int *cell_start = a.take<int>(cap_fine + 4);
   int *cell_id = a.take<int>(N);
   int *slot = a.take<int>(N);
+  int *order = a.take<int>(N);
+  int *rank = a.take<int>(N);
   float4 *sorted = a.take<float4>(N);
   if (!a.ok) {
     set_error("knn: workspace too small (%zu bytes given, %zu needed)", workspace_bytes, knn_grid_workspace_bytes(N));
@@ -535,19 +546,24 @@ int knn_grid_build(const float *xyz, int N, int k, void *workspace, size_t works
   GF_LAUNCHED();
   knn_scan_kernel<<<KNN_SCAN_BLOCKS, 256, 0, st>>>(ctl, cell_count, cell_start, N);
   GF_LAUNCHED();
-  knn_scatter_kernel<<<npt, 256, 0, st>>>(xyz, N, cell_id, slot, cell_start, sorted);
+  knn_scatter_kernel<<<npt, 256, 0, st>>>(xyz, N, cell_id, slot, cell_start, sorted, order, rank);
   GF_LAUNCHED();
   out->grid = g;
   out->cell_start = cell_start;
   out->sorted = sorted;
+  out->order = order;
+  out->rank = rank;
   return GF_OK;
 }
 
 int knn_grid_query(const KnnGridBuffers &b, const float *queries, int nq, int k, int do_sqrt, float *dist,
                    long long *idx64, int *idx32, cudaStream_t st, const KnnEdgeOut *edges) {
   const KnnGrid *g = (const KnnGrid *)b.grid;
-  KnnEdgeOut eo = {nullptr, nullptr, 0.f, 0, 0};
-  if (edges && queries == nullptr) eo = *edges;
+  KnnEdgeOut eo = {nullptr, nullptr, 0.f, 0, nullptr};
+  if (edges && queries == nullptr) {
+    eo = *edges;
+    if (eo.rank) eo.rank = b.rank;  // any non-null value asks for the cell-order format
+  }
   if (k <= 8)
     launch_grid_query<8>(g, b.sorted, b.cell_start, queries, nq, k, do_sqrt, dist, idx64, idx32, eo, st);
   else if (k <= 16)

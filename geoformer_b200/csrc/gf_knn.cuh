@@ -10,6 +10,8 @@ struct KnnGridBuffers {
   const void *grid;       // device KnnGrid
   const int *cell_start;  // (ncells+1) exclusive prefix of the cell populations
   const float4 *sorted;   // (N) points in cell order: x, y, z, bit-cast original index
+  const int *order;       // (N) order[cell-order position] = original index
+  const int *rank;        // (N) rank[original index] = cell-order position
 };
 
 // optional second output of the self query: the propagation's packed edge table (gf_geodesic.cuh)
@@ -18,7 +20,8 @@ struct KnnEdgeOut {
   float *len;  // (N + 1) << slot_bits
   float radius;
   int slot_bits;
-  int enc;  // != 0: targets stored as (t >> 5) << 7 | (t & 31) (gf_geodesic.cu: geo_enc_target)
+  const int *rank;  // != nullptr: table in CELL ORDER (rows and targets are cell-order positions), targets stored
+                    // encoded as (t >> 5) << 7 | (t & 31) (gf_geodesic.cu); nullptr: original indices, plain
 };
 
 size_t knn_grid_workspace_bytes(int N);
