@@ -34,6 +34,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# hardware work queues: the pipeline keeps ~20 streams busy (two batches in flight x (4 FPS + 4 kNN lanes), copy lanes
+# of the host path); with the default of 8 connections unrelated streams share a queue and wait for each other
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 N_SCENES = 8  # rotating scenes per rank (both arms)
 
@@ -46,14 +49,16 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
     ap.add_argument("--max-step", type=int, default=None, help="override the workload's level bound")
-    ap.add_argument("--batch", type=int, default=4, help="scenes per library call (reduced to a divisor of --steps)")
+    ap.add_argument("--batch", type=int, default=10, help="scenes per library call (reduced to a divisor of --steps)")
     ap.add_argument("--repeats", type=int, default=0, help="repetitions of the K-step timed region (0 = automatic)")
     ap.add_argument("--runners", type=int, default=2, help="batches in flight (alternating CUDA streams)")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
-    ap.add_argument("--seed-sharded", default=None, choices=["nccl", "fused"],
+    ap.add_argument("--seed-sharded", default=None, choices=["shard", "nccl", "fused"],
                     help="ONE scene split by seed blocks over the ranks (SURVEY 8(e), strong scaling): row blocks "
                          "exchanged by an NCCL all-gather, or stored into the peers by the propagation kernel itself")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-threads", type=int, default=2, help="blocking host-buffer calls in flight")
+    ap.add_argument("--e2e-batch", type=int, default=4, help="scenes per host-buffer call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip epilogues / eval setting / model setting records")
     return ap.parse_args()
@@ -283,46 +288,62 @@ def bind_to_gpu_numa_node(local):
 
 # ------------------------------------------------------------------------------------------------
 def seed_sharded_record(cfg4, mode, steps, dist, dev, rank, world):
-    """One c4 scene split by seed blocks over the ranks; returns the sub-record on rank 0."""
+    """One c4 scene (1M points, 512 seeds) split by seed blocks over the ranks, next to the
+    same scene on ONE GPU measured in the same process.  mode "shard": every rank keeps its (Q/G, N) block, no
+    exchange (the mode that scales); "fused" / "nccl": the full matrix on every rank, rows stored into the peers by
+    the propagation kernel / gathered by NCCL.  Returns the sub-record (identical on all ranks)."""
     import torch
 
-    from geoformer_b200.parallel import SeedShardedRows, seed_sharded_guidance, seed_sharded_guidance_fused
+    from geoformer_b200.guidance import GuidanceRunner
+    from geoformer_b200.parallel import (SeedShardedRows, seed_sharded_guidance, seed_sharded_guidance_fused,
+                                         shard_seeds)
 
     N, Q, k = cfg4["n"], cfg4["Q"], cfg4["k"]
     x = make_scene(cfg4, 0).to(dev)
-    rows = SeedShardedRows(Q, N) if mode == "fused" else None
 
-    def step():
+    def timed(fn, n):
+        for _ in range(3):
+            out = fn()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    one = GuidanceRunner(N, Q, k, cfg4["radius"], cfg4["max_step"], device=dev)
+    ms_one, out_one = timed(lambda: one.run(x), steps)
+    q0, q1 = shard_seeds(Q, rank, world)
+    want = out_one[1][q0:q1].clone()
+    del one, out_one
+    torch.cuda.empty_cache()
+    rec = {"workload": "c4: room(n=%d), Q=%d, k=%d, radius=%.3g, max_step=%d" % (N, Q, k, cfg4["radius"], cfg4["max_step"]),
+           "world": world, "steps": steps, "one_gpu_ms_per_scene": ms_one}
+    for m in (["shard", mode] if mode != "shard" else ["shard"]):
+        rows = SeedShardedRows(Q, N) if m == "fused" else None
+        if m == "shard":
+            fn = lambda: seed_sharded_guidance(x, Q, k, cfg4["radius"], cfg4["max_step"], gather=False)  # noqa: E731
+        elif m == "fused":
+            fn = lambda: seed_sharded_guidance_fused(x, Q, k, cfg4["radius"], cfg4["max_step"], rows)  # noqa: E731
+        else:
+            fn = lambda: seed_sharded_guidance(x, Q, k, cfg4["radius"], cfg4["max_step"])  # noqa: E731
+        ms, out = timed(fn, steps)
+        mine = out[1] if m == "shard" else out[1][q0:q1]
+        same = torch.tensor([1 if torch.equal(mine, want) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        rec[m] = {"ms_per_scene": ms, "maps_per_s": Q / (ms * 1e-3), "speedup_vs_one_gpu": ms_one / ms,
+                  "rows_identical_to_the_one_gpu_run_on_all_ranks": bool(same.item())}
+        del out, mine
         if rows is not None:
-            return seed_sharded_guidance_fused(x, Q, k, cfg4["radius"], cfg4["max_step"], rows)
-        return seed_sharded_guidance(x, Q, k, cfg4["radius"], cfg4["max_step"])
-
-    for _ in range(3):
-        out = step()
-    torch.cuda.synchronize(dev)
-    checksum = float(out[1].double().sum().item())
-    dist.barrier()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    dist.barrier()
-    torch.cuda.synchronize(dev)
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    cs = torch.tensor([checksum], device=dev, dtype=torch.float64)
-    lo, hi = cs.clone(), cs.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    if rows is not None:
-        rows.close()
-    del x
-    return {"workload": "c4: room(n=%d), Q=%d, k=%d" % (N, Q, k), "exchange": mode, "world": world,
-            "ms_per_scene": float(t.item()) / steps, "steps": steps,
-            "maps_per_s": Q / (float(t.item()) / steps * 1e-3),
-            "result_identical_on_all_ranks": bool(lo.item() == hi.item()), "checksum": checksum}
+            rows.close()
+        torch.cuda.empty_cache()
+    return rec
 
 
 def run_seed_sharded(args):
@@ -346,12 +367,13 @@ def run_seed_sharded(args):
     rec = seed_sharded_record(cfg, args.seed_sharded, K, dist, dev, rank, world)
     clocks = sampler.stop()
     if rank == 0:
+        main = rec[args.seed_sharded]
         print(json.dumps({
-            "metric": "geodesic maps/sec", "value": rec["maps_per_s"], "unit": "maps/s", "n_gpus": world, "steps": K,
-            "warmup": 3, "ms_per_step": rec["ms_per_scene"], "higher_is_better": True, "scaling": "strong",
+            "metric": "geodesic maps/sec", "value": main["maps_per_s"], "unit": "maps/s", "n_gpus": world, "steps": K,
+            "warmup": 3, "ms_per_step": main["ms_per_scene"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(cfg, args),
             "parallelism": "seed-sharded x%d, exchange: %s" % (world, args.seed_sharded), "clocks": clocks,
-            "result_identical_on_all_ranks": rec["result_identical_on_all_ranks"], "checksum": rec["checksum"],
+            "seed_sharded": rec,
         }), flush=True)
     dist.destroy_process_group()
     return 0
@@ -560,17 +582,28 @@ def run_ours(args):
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------
     e2e = None
     if not args.no_e2e:
+        from geoformer_b200.guidance import HostBatchGuidance
+
         pinned = [x.pin_memory() for x in scenes_host]
-        nthreads = 4
-        hgs = [HostGuidance(N, Q, k, cfg["radius"], cfg["max_step"], device=dev) for _ in range(nthreads)]
-        Ke = max(4, min(K, 32))
+        Be = max(1, min(args.e2e_batch, 16)) if batched else 1
+        nthreads = max(1, args.e2e_threads)  # blocking calls in flight (a call overlaps its own copies and compute)
+        if batched:
+            hgs = [HostBatchGuidance(N, Be, Q, k, cfg["radius"], cfg["max_step"], device=dev) for _ in range(nthreads)]
+            run_one = lambda h, c: h.run([pinned[(c * Be + b) % S] for b in range(Be)])  # noqa: E731
+            call_name = "gf_guidance_batch_host (%d scenes per call" % Be
+        else:
+            hgs = [HostGuidance(N, Q, k, cfg["radius"], cfg["max_step"], device=dev) for _ in range(nthreads)]
+            run_one = lambda h, c: h.run(pinned[c % S])  # noqa: E731
+            call_name = "gf_guidance_host (1 scene per call"
+        Ke = (40 // Be) * Be if batched else 8  # scenes: the copy of the maps is the bound; a fixed count keeps fill / drain small
+        ncalls = Ke // Be
         for h in hgs:
-            h.run(pinned[0])
+            run_one(h, 0)
 
         def worker(tid):
             torch.cuda.set_device(local)
-            for i in range(tid, Ke, nthreads):
-                hgs[tid].run(pinned[i % S])
+            for c in range(tid, ncalls, nthreads):
+                run_one(hgs[tid], c)
 
         barrier()
         t0 = time.perf_counter()
@@ -585,16 +618,17 @@ def run_ours(args):
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        # what the link alone gives: the same 102 MB of maps copied device -> pinned host, nothing else running
+        # what the link alone gives: the same maps copied device -> pinned host, nothing else running
         link = None
         try:
             src = torch.empty((Q, N), dtype=torch.float32, device=dev)
+            dst = hgs[0].geo_host[0] if batched else hgs[0].geo_host
             a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            hgs[0].geo_host.copy_(src, non_blocking=True)
+            dst.copy_(src, non_blocking=True)
             torch.cuda.synchronize(dev)
             a_.record()
             for _ in range(4):
-                hgs[0].geo_host.copy_(src, non_blocking=True)
+                dst.copy_(src, non_blocking=True)
             b_.record()
             torch.cuda.synchronize(dev)
             link = 4.0 * Q * N * 4 / (a_.elapsed_time(b_) * 1e-3) / 1e9
@@ -605,7 +639,7 @@ def run_ours(args):
                "d2h_link_GBps": link,
                "d2h_achieved_GBps": hgs[0].d2h_bytes * Ke / dt / 1e9,
                "d2h_bytes_per_step": hgs[0].d2h_bytes, "steps": Ke, "ms_per_step": 1e3 * dt / Ke,
-               "call": "gf_guidance_host (pinned host buffers, %d overlapped host threads)" % nthreads}
+               "call": call_name + ", pinned host buffers, %d overlapped host threads)" % nthreads}
         del hgs
 
     # ---- one large scene split by seed blocks over the ranks, multi-rank runs only --------
@@ -620,6 +654,8 @@ def run_ours(args):
             runners = []
             torch.cuda.empty_cache()
             sharded = seed_sharded_record(dict(CONFIGS["c4"]), "fused", 6, dist, dev, rank, world)
+            if rank != 0:
+                sharded = None
         except Exception as ex:
             sharded = {"error": repr(ex)}
 

@@ -54,6 +54,7 @@ SIGNATURES = {
     "gf_guidance_seeded": (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gf_guidance_batch_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
     "gf_guidance_batch": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "gf_guidance_shard": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gf_geodesic_scatter": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_int, _P, _P, c_int, _P, _P,
                                     c_size_t, _P]),
     "gf_guidance_seeded_scatter": (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, c_int, _P, _P,
@@ -63,6 +64,8 @@ SIGNATURES = {
     "gf_peer_export": (c_int, [_P, _P]),
     "gf_peer_open": (c_int, [_P, _P]),
     "gf_peer_close": (c_int, [_P]),
+    "gf_guidance_batch_host_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
+    "gf_guidance_batch_host": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
     "gf_guidance_host_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gf_guidance_host": (c_int, [_P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
 }

@@ -596,12 +596,18 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
     while (F > 0 && level < a.max_step) {
       ++level;
       GF_TR(0);
-      // first stage of this thread's own resolve: the key of its first frontier point (final since the barrier)
-      int rt = -1;
-      uint32_t rkey = 0;
-      if (level > 1 && (int)tid < F) {
-        rt = frontier((int)tid, (level - 1) & 1);
-        rkey = ld_cg_u32(claim + rt);
+      // first stage of this thread's own resolves: the keys of its first two frontier points (final since the barrier)
+      int rt[2] = {-1, -1};
+      uint32_t rkey[2] = {0u, 0u};
+      if (level > 1) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = (int)tid + u * THREADS;
+          if (i < F) {
+            rt[u] = frontier(i, (level - 1) & 1);
+            rkey[u] = ld_cg_u32(claim + rt[u]);
+          }
+        }
       }
       // ---- claims: KP/4 lanes per frontier point; lanes past the end expand the sentinel point N -------------
       const int Fs = F < QC ? F : QC;
@@ -632,62 +638,71 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
       GF_TR(1);
       // ---- the frontier's own distances (its points were won at level-1 and still hold their keys) ----------
       if (level > 1) {
-        float rw = 0.f, rpd = 0.f;
-        if (rt >= 0) {  // second stage: the loads below are in flight while the rest of the frontier is resolved
-          claim[rt] = GEO_UNCLAIMED;
-          const unsigned po = rkey >> sb, j = rkey & (KP - 1);
-          const unsigned p = rank ? (unsigned)__ldg(rank + po) : po;
-          rw = __ldg(S.len + ((size_t)p << sb) + j);
-          if (level > 2) rpd = __ldcg(dist + p);
-        }
-        for (int i = (int)tid + THREADS; i < F; i += THREADS) resolve(frontier(i, (level - 1) & 1), level - 1);
-        if (rt >= 0) {
-          const float d = level == 2 ? rw : __fadd_rn(rw, rpd);
-          dist[rt] = d;
-          rmax = fmaxf(rmax, d);
-        }
+        // second stage: the two dependent round trips (rank of the winning parent, then its edge length and
+        // distance) of both points are in flight together
+        unsigned rp[2] = {0u, 0u};
+        float rw[2] = {0.f, 0.f}, rpd[2] = {0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (rt[u] >= 0) {
+            claim[rt[u]] = GEO_UNCLAIMED;
+            const unsigned po = rkey[u] >> sb;
+            rp[u] = rank ? (unsigned)__ldg(rank + po) : po;
+          }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (rt[u] >= 0) {
+            rw[u] = __ldg(S.len + ((size_t)rp[u] << sb) + (rkey[u] & (KP - 1)));
+            if (level > 2) rpd[u] = __ldcg(dist + rp[u]);
+          }
+        for (int i = (int)tid + 2 * THREADS; i < F; i += THREADS) resolve(frontier(i, (level - 1) & 1), level - 1);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (rt[u] >= 0) {
+            const float d = level == 2 ? rw[u] : __fadd_rn(rw[u], rpd[u]);
+            dist[rt[u]] = d;
+            rmax = fmaxf(rmax, d);
+          }
       }
       GF_TR(2);
       __syncthreads();
       GF_TR(3);
       // ---- commit: the points claimed at this level become visited (:140) and form the next frontier -------
       if (tid == 0) s_next_n[(level + 1) & 1] = 0;  // idle since the previous level's reads; used after the next barrier
-      if (level == 1 && seed_ok && tid == (((unsigned)s >> 7) & (THREADS - 1))) {
+      if (level == 1 && seed_ok && tid == (((unsigned)s >> 5) & (THREADS - 1))) {  // the owner of the seed's word
         // the seed joins the visited set now; if no self edge re-won it, its distance stays 0
         // (a re-won seed holds its key until it is resolved with the other level-1 points)
         if (ld_cg_u32(claim + s) == GEO_UNCLAIMED) dist[s] = 0.f;
         vis[(unsigned)s >> 5] |= 1u << (s & 31);
       }
       {
-        uint4 *clm4 = reinterpret_cast<uint4 *>(clm), *vis4 = reinterpret_cast<uint4 *>(vis);
-        const int n4 = words >> 2;  // a multiple of 4 words
+        // Every thread owns single 32-bit words of the bitmaps, consecutive words to consecutive threads: claimed ->
+        // visited, claimed cleared, one counter atomic per non-empty word, the set bits enumerated into the queue.
+        // In cell order the claimed bits come in dense runs (a frontier is a shell in space: two short runs per row
+        // of cells): with 16-byte pieces a run fell to one lane looping 50+ times while the CTA waited at the
+        // barrier, and the rows of a shell to a few warps; word by word a run spreads over neighbouring lanes and the
+        // shell over all warps.
         int *cnt = &s_next_n[level & 1];
         const int par = level & 1;
-        for (int i = tid; i < n4; i += THREADS) {
-          const uint4 c = clm4[i];
-          if ((c.x | c.y | c.z | c.w) == 0u) continue;
-          clm4[i] = make_uint4(0u, 0u, 0u, 0u);
-          uint4 v = vis4[i];
-          v.x |= c.x, v.y |= c.y, v.z |= c.z, v.w |= c.w;
-          vis4[i] = v;
-          const int n = __popc(c.x) + __popc(c.y) + __popc(c.z) + __popc(c.w);
+        for (int j = tid; j < words; j += THREADS) {
+          const uint32_t c = clm[j];
+          if (c == 0u) continue;
+          clm[j] = 0u;
+          vis[j] |= c;
+          const int n = __popc(c);
           int at = atomicAdd(cnt, n);
-          const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
-          if (at + n <= QC) {  // the usual case: the whole piece lands in the on-chip queue
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              for (uint32_t m = cw[k4]; m; m &= m - 1) fq[at++] = i * 128 + k4 * 32 + __ffs((int)m) - 1;
+          const int base = j * 32;
+          if (at + n <= QC) {  // the usual case: all of the word's points land in the on-chip queue
+            for (uint32_t m = c; m; m &= m - 1) fq[at++] = base + __ffs((int)m) - 1;
           } else {
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              for (uint32_t m = cw[k4]; m; m &= m - 1) {
-                const int t = i * 128 + k4 * 32 + __ffs((int)m) - 1;
-                if (at < QC)
-                  fq[at] = t;
-                else
-                  ovf[ovf_at(at, par)] = t;
-                ++at;
-              }
+            for (uint32_t m = c; m; m &= m - 1) {
+              const int t = base + __ffs((int)m) - 1;
+              if (at < QC)
+                fq[at] = t;
+              else
+                ovf[ovf_at(at, par)] = t;
+              ++at;
+            }
           }
         }
       }
@@ -784,7 +799,7 @@ struct GeoPlan {
 };
 
 // shared-memory plan, identical for sizing and launching: 227 KB usable per SM on sm_100 (1 KB reserved per CTA)
-static void geo_smem_plan(int N, GeoPlan *p, int *ctas_per_sm) {
+static void geo_smem_plan(int N, int Q, GeoPlan *p, int *ctas_per_sm) {
   const int words = geo_bitmap_words(N);
   static const int nobitmap = env_int("GF_GEO_NOBITMAP", 0);  // test knob: 1 = no on-chip state, 2 = visited bitmap only
   static const int force_threads = env_int("GF_GEO_THREADS", 0);
@@ -793,8 +808,9 @@ static void geo_smem_plan(int N, GeoPlan *p, int *ctas_per_sm) {
     return sizeof(int) * (size_t)(mode == 2 ? 1 : 2) * GEO_QCAP + sizeof(uint32_t) * (size_t)mode * words;
   };
   // both bitmaps must fit for mode 2; otherwise mode 0 (two CTAs per SM) measured slightly faster at 1 M
-  // points than mode 1 (157 KB of shared memory: one CTA per SM), which stays available through the knob
-  if (m == 2 && bytes_of(2) > (size_t)226 * 1024) m = 0;
+  // points and 512 seeds than mode 1 (157 KB of shared memory: one CTA per SM).  With no more seeds than SMs (a
+  // rank's block of a seed-sharded scene) one CTA per SM loses nothing and the visited test stays on chip: mode 1.
+  if (m == 2 && bytes_of(2) > (size_t)226 * 1024) m = (Q <= num_sms() && nobitmap == 0) ? 1 : 0;
   if (m == 1 && bytes_of(1) > (size_t)226 * 1024) m = 0;
   const size_t bytes = bytes_of(m);
   int fit = (int)((size_t)(227 * 1024) / (bytes + 1024));
@@ -810,7 +826,7 @@ static void geo_smem_plan(int N, GeoPlan *p, int *ctas_per_sm) {
 
 static void plan_geo(int N, int Q, GeoPlan *p) {
   int per_sm = 1;
-  geo_smem_plan(N, p, &per_sm);
+  geo_smem_plan(N, Q, p, &per_sm);
   static const int bps_cap = env_int("GF_GEO_BPS", 0);  // experiment knob
   if (bps_cap > 0 && per_sm > bps_cap) per_sm = bps_cap;
   int grid = num_sms() * per_sm;

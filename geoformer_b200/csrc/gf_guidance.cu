@@ -23,7 +23,7 @@ struct ForkJoin {
   cudaEvent_t join = nullptr;  // = join_fps[0]
 };
 
-static int get_fork_join(cudaStream_t user, ForkJoin **out) {
+static int get_fork_join(cudaStream_t user, ForkJoin **out, int lanes_needed = 1) {
   constexpr int SLOTS = 16;
   struct Entry {
     int dev;
@@ -47,18 +47,8 @@ static int get_fork_join(cudaStream_t user, ForkJoin **out) {
       if (e->dev != dev) e = nullptr;
     }
     if (e && !e->used) {
-      int lo = 0, hi = 0;
-      GF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = greatest priority
-      ForkJoin &f = e->fj;
-      GF_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
-      for (int l = 0; l < LANES; ++l) {
-        GF_CUDA(cudaStreamCreateWithPriority(&f.fps[l], cudaStreamNonBlocking, hi));
-        GF_CUDA(cudaEventCreateWithFlags(&f.join_fps[l], cudaEventDisableTiming));
-        if (l > 0) GF_CUDA(cudaStreamCreateWithPriority(&f.knn[l], cudaStreamNonBlocking, lo));
-        GF_CUDA(cudaEventCreateWithFlags(&f.join_knn[l], cudaEventDisableTiming));
-      }
-      f.aux = f.fps[0];
-      f.join = f.join_fps[0];
+      e->fj = ForkJoin();
+      GF_CUDA(cudaEventCreateWithFlags(&e->fj.fork, cudaEventDisableTiming));
       e->used = true;
       e->dev = dev;
     }
@@ -68,6 +58,21 @@ static int get_fork_join(cudaStream_t user, ForkJoin **out) {
     set_error("guidance: no auxiliary stream available on device %d", dev);
     return GF_ERR_CUDA;
   }
+  // Lanes are created on first use: every stream beyond the device's hardware queues (CUDA_DEVICE_MAX_CONNECTIONS,
+  // 8 by default) shares a queue with another one and inherits false dependencies -- a single-scene call needs
+  // exactly one auxiliary stream, only a batch of four or more scenes all of them.
+  ForkJoin &f = e->fj;
+  for (int l = 0; l < lanes_needed && l < LANES; ++l) {
+    if (f.fps[l]) continue;
+    int lo = 0, hi = 0;
+    GF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = greatest priority
+    GF_CUDA(cudaStreamCreateWithPriority(&f.fps[l], cudaStreamNonBlocking, hi));
+    GF_CUDA(cudaEventCreateWithFlags(&f.join_fps[l], cudaEventDisableTiming));
+    if (l > 0) GF_CUDA(cudaStreamCreateWithPriority(&f.knn[l], cudaStreamNonBlocking, lo));
+    GF_CUDA(cudaEventCreateWithFlags(&f.join_knn[l], cudaEventDisableTiming));
+  }
+  f.aux = f.fps[0];
+  f.join = f.join_fps[0];
   *out = &e->fj;
   return GF_OK;
 }
@@ -98,8 +103,11 @@ extern "C" size_t gf_guidance_workspace_bytes(int N, int Q, int k) {
 static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, int max_step, int *seeds,
                          int seeds_given, float *geo, float *knn_dist, int32_t *knn_idx32, int64_t *stats,
                          void *workspace, size_t workspace_bytes, void *stream, float *const *peer_geo = nullptr,
-                         int n_peers = 0, float *row_max = nullptr) {
+                         int n_peers = 0, float *row_max = nullptr, int q0 = 0, int q1 = -1) {
+  // [q0, q1): the block of seeds that is propagated here (all of them by default); FPS always samples all Q
+  if (q1 < 0) q1 = Q;
   GF_CHECK_ARG(N >= 1 && Q >= 1, "guidance: need N >= 1 and Q >= 1 (N=%d Q=%d)", N, Q);
+  GF_CHECK_ARG(q0 >= 0 && q0 <= q1 && q1 <= Q, "guidance: seed block [%d, %d) outside [0, %d)", q0, q1, Q);
   GF_CHECK_ARG(k >= 1 && k <= KNN_MAX_K, "guidance: k=%d outside [1,%d]", k, KNN_MAX_K);
   GF_CHECK_ARG(xyz && seeds && geo, "guidance: null pointer");
   GuidancePlan p = plan_guidance(N, Q, k);
@@ -138,6 +146,7 @@ static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, in
   KnnEdgeOut eo;
   eo.radius = radius;
   int enc = 0;
+  const int Qb = q1 - q0;  // the workspace was sized for Q >= Qb seeds: enough for any block
   rc = geodesic_edge_buffers(ws_geo, p.geo, N, k, Q, &eo.tgt, &eo.len, &eo.slot_bits, &enc);
   if (rc) return rc;
   if (n_peers > 0) enc = 0;  // seed-sharded scenes run the per-scene kernel: original numbering, plain targets
@@ -147,8 +156,9 @@ static int guidance_impl(const float *xyz, int N, int Q, int k, float radius, in
   // join, then propagate
   if (!seeds_given) GF_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   stage_mark(ST_KNN_DONE, st);
-  return geodesic_run(nullptr, nullptr, /*is64=*/0, N, k, seeds, Q, radius, max_step, geo, stats, ws_geo, p.geo, st,
-                      peer_geo, n_peers, row_max, enc ? gb.rank : nullptr, enc ? gb.order : nullptr);
+  if (Qb == 0) return GF_OK;
+  return geodesic_run(nullptr, nullptr, /*is64=*/0, N, k, seeds + q0, Qb, radius, max_step, geo, stats, ws_geo, p.geo,
+                      st, peer_geo, n_peers, row_max, enc ? gb.rank : nullptr, enc ? gb.order : nullptr);
 }
 
 extern "C" int gf_guidance(const float *xyz, int N, int Q, int k, float radius, int max_step, int *seeds, float *geo,
@@ -163,6 +173,13 @@ extern "C" int gf_guidance_seeded(const float *xyz, int N, const int *seeds, int
                                   void *workspace, size_t workspace_bytes, void *stream) {
   return guidance_impl(xyz, N, Q, k, radius, max_step, const_cast<int *>(seeds), 1, geo, knn_dist, knn_idx32, stats,
                        workspace, workspace_bytes, stream, nullptr, 0, row_max);
+}
+
+extern "C" int gf_guidance_shard(const float *xyz, int N, int Q, int q0, int q1, int k, float radius, int max_step,
+                                 int *seeds, float *geo_block, int64_t *stats, float *row_max_block, void *workspace,
+                                 size_t workspace_bytes, void *stream) {
+  return guidance_impl(xyz, N, Q, k, radius, max_step, seeds, 0, geo_block, nullptr, nullptr, stats, workspace,
+                       workspace_bytes, stream, nullptr, 0, row_max_block, q0, q1);
 }
 
 extern "C" int gf_guidance_seeded_scatter(const float *xyz, int N, const int *seeds, int Q, int k, float radius,
@@ -237,10 +254,10 @@ extern "C" int gf_guidance_batch(const float *const *xyz, const int *Ns, int B, 
   cudaStream_t st = (cudaStream_t)stream;
   char *w = (char *)workspace;
   ForkJoin *fj = nullptr;
-  int rc = get_fork_join(st, &fj);
+  const int lanes = B < LANES ? B : LANES;
+  int rc = get_fork_join(st, &fj, lanes);
   if (rc) return rc;
   stage_mark(ST_BEGIN, st);
-  const int lanes = B < LANES ? B : LANES;
   GF_CUDA(cudaEventRecord(fj->fork, st));
   for (int l = 0; l < lanes; ++l) {
     if (!seeds_given) GF_CUDA(cudaStreamWaitEvent(fj->fps[l], fj->fork, 0));
@@ -324,6 +341,106 @@ extern "C" int gf_guidance_host(const float *xyz_host, int N, int Q, int k, floa
   if (rc) return rc;
   GF_CUDA(cudaMemcpyAsync(seeds_host, d_seeds, sizeof(int) * (size_t)Q, cudaMemcpyDeviceToHost, st));
   GF_CUDA(cudaMemcpyAsync(geo_host, d_geo, sizeof(float) * (size_t)Q * N, cudaMemcpyDeviceToHost, st));
+  GF_CUDA(cudaStreamSynchronize(st));
+  return GF_OK;
+}
+
+// ---- host-buffer variant of the batched call (what bench.py's `e2e` number times) ---------------------------------
+// The maps are 4*Q*N bytes per scene: at PCIe speed their copy takes several times as long as computing them, so
+// the call is organised around the LINK: the scenes go one by one over two internal lanes (copy in -> hot path ->
+// copy out), lane l + 1 computes while lane l's maps travel, and the device -> host copies follow each other without
+// a gap.  (The one-launch batched propagation would deliver all maps at once, after the last scene's compute.)
+namespace gf {
+constexpr int HOST_LANES = 2;
+struct HostLanes {
+  cudaStream_t lane[HOST_LANES] = {};
+  cudaEvent_t fork = nullptr, join[HOST_LANES] = {};
+};
+static int get_host_lanes(HostLanes **out) {
+  static thread_local HostLanes pool[8];
+  static thread_local bool used[8] = {};
+  int dev = 0;
+  GF_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 8) dev = 0;
+  HostLanes &h = pool[dev];
+  if (!used[dev]) {
+    GF_CUDA(cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming));
+    for (int l = 0; l < HOST_LANES; ++l) {
+      GF_CUDA(cudaStreamCreateWithFlags(&h.lane[l], cudaStreamNonBlocking));
+      GF_CUDA(cudaEventCreateWithFlags(&h.join[l], cudaEventDisableTiming));
+    }
+    used[dev] = true;
+  }
+  *out = &h;
+  return GF_OK;
+}
+
+struct HostBatchPlan {
+  size_t xyz[GEO_BATCH_MAX], seeds[GEO_BATCH_MAX], geo[GEO_BATCH_MAX], lane_ws[HOST_LANES], lane_bytes, total;
+};
+static void plan_host_batch(const int *Ns, int B, int Q, int k, HostBatchPlan *p) {
+  size_t off = 0;
+  int maxN = 1;
+  for (int b = 0; b < B; ++b) {
+    p->xyz[b] = off, off += align256(sizeof(float) * 3 * (size_t)Ns[b]);
+    p->seeds[b] = off, off += align256(sizeof(int) * (size_t)Q);
+    p->geo[b] = off, off += align256(sizeof(float) * (size_t)Q * Ns[b]);
+    maxN = Ns[b] > maxN ? Ns[b] : maxN;
+  }
+  p->lane_bytes = align256(plan_guidance(maxN, Q, k).total);
+  for (int l = 0; l < HOST_LANES; ++l) p->lane_ws[l] = off, off += p->lane_bytes;
+  p->total = off + 1024;
+}
+}  // namespace gf
+
+extern "C" size_t gf_guidance_batch_host_workspace_bytes(const int *Ns, int B, int Q, int k) {
+  if (!Ns || B <= 0 || B > GEO_BATCH_MAX || Q <= 0 || k <= 0) return 0;
+  for (int b = 0; b < B; ++b)
+    if (Ns[b] <= 0) return 0;
+  HostBatchPlan p;
+  plan_host_batch(Ns, B, Q, k, &p);
+  return p.total;
+}
+
+extern "C" int gf_guidance_batch_host(const float *const *xyz_host, const int *Ns, int B, int Q, int k, float radius,
+                                      int max_step, int *const *seeds_host, float *const *geo_host, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
+  GF_CHECK_ARG(xyz_host && Ns && seeds_host && geo_host, "guidance_batch_host: null pointer array");
+  GF_CHECK_ARG(B >= 1 && B <= GEO_BATCH_MAX && Q >= 1, "guidance_batch_host: B=%d Q=%d", B, Q);
+  GF_CHECK_ARG(k >= 1 && k <= KNN_MAX_K, "guidance_batch_host: k=%d outside [1,%d]", k, KNN_MAX_K);
+  for (int b = 0; b < B; ++b)
+    GF_CHECK_ARG(Ns[b] >= 1 && xyz_host[b] && seeds_host[b] && geo_host[b], "guidance_batch_host: scene %d: empty or null", b);
+  HostBatchPlan p;
+  plan_host_batch(Ns, B, Q, k, &p);
+  if (workspace == nullptr || workspace_bytes < p.total) {
+    set_error("guidance_batch_host: workspace too small (%zu bytes given, %zu needed)", workspace_bytes, p.total);
+    return GF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char *w = (char *)workspace;
+  HostLanes *hl = nullptr;
+  int rc = get_host_lanes(&hl);
+  if (rc) return rc;
+  const int lanes = B < HOST_LANES ? B : HOST_LANES;
+  GF_CUDA(cudaEventRecord(hl->fork, st));
+  for (int l = 0; l < lanes; ++l) GF_CUDA(cudaStreamWaitEvent(hl->lane[l], hl->fork, 0));
+  for (int b = 0; b < B; ++b) {
+    const int l = b % lanes;
+    cudaStream_t ls = hl->lane[l];
+    float *d_xyz = (float *)(w + p.xyz[b]);
+    int *d_seeds = (int *)(w + p.seeds[b]);
+    float *d_geo = (float *)(w + p.geo[b]);
+    GF_CUDA(cudaMemcpyAsync(d_xyz, xyz_host[b], sizeof(float) * 3 * (size_t)Ns[b], cudaMemcpyHostToDevice, ls));
+    rc = gf_guidance(d_xyz, Ns[b], Q, k, radius, max_step, d_seeds, d_geo, nullptr, nullptr, nullptr, nullptr,
+                     w + p.lane_ws[l], p.lane_bytes, ls);
+    if (rc) return rc;
+    GF_CUDA(cudaMemcpyAsync(seeds_host[b], d_seeds, sizeof(int) * (size_t)Q, cudaMemcpyDeviceToHost, ls));
+    GF_CUDA(cudaMemcpyAsync(geo_host[b], d_geo, sizeof(float) * (size_t)Q * Ns[b], cudaMemcpyDeviceToHost, ls));
+  }
+  for (int l = 0; l < lanes; ++l) {
+    GF_CUDA(cudaEventRecord(hl->join[l], hl->lane[l]));
+    GF_CUDA(cudaStreamWaitEvent(st, hl->join[l], 0));
+  }
   GF_CUDA(cudaStreamSynchronize(st));
   return GF_OK;
 }

@@ -284,3 +284,39 @@ class HostGuidance:
                                              C.ptr(self._ws), self._nbytes,
                                              ctypes.c_void_p(self.stream.cuda_stream)), "guidance_host")
         return self.seeds_host, self.geo_host
+
+
+class HostBatchGuidance:
+    """Host-buffer entry point for batches: run(list of B pinned (N,3) CPU tensors) copies the points to the device,
+    runs the batched hot path and copies seeds and maps back, all inside gf_guidance_batch_host (blocking; releases
+    the GIL).  Two objects driven from two Python threads keep the host link busy: the maps of one batch (4*Q*N bytes
+    per scene) travel while the next batch is computed."""
+
+    def __init__(self, N, B, n_queries, neighbor, radius, max_step, device="cuda", pinned=True):
+        self.N, self.B, self.Q, self.k = int(N), int(B), int(n_queries), int(neighbor)
+        self.radius, self.max_step = float(radius), int(max_step)
+        self.device = torch.device(device)
+        self._L = C.lib()
+        self._Ns = (ctypes.c_int * self.B)(*([self.N] * self.B))
+        self._nbytes = self._L.gf_guidance_batch_host_workspace_bytes(self._Ns, self.B, self.Q, self.k)
+        C.require(self._nbytes > 0, "scenes of %d points do not fit the batched call" % self.N)
+        self._ws = torch.empty(self._nbytes, dtype=torch.uint8, device=self.device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.seeds_host = torch.empty((self.B, self.Q), dtype=torch.int32, pin_memory=pinned)
+        self.geo_host = torch.empty((self.B, self.Q, self.N), dtype=torch.float32, pin_memory=pinned)
+        self._seeds_p = _ptr_array([self.seeds_host[b] for b in range(self.B)])
+        self._geo_p = _ptr_array([self.geo_host[b] for b in range(self.B)])
+        self.h2d_bytes = self.N * 3 * 4  # per scene
+        self.d2h_bytes = self.Q * 4 + self.Q * self.N * 4
+
+    def run(self, scenes_host):
+        C.require(len(scenes_host) == self.B, "need %d scenes" % self.B)
+        for x in scenes_host:
+            C.require(not x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (self.N, 3),
+                      "scenes must be contiguous float32 CPU tensors of shape (N, 3)")
+        with torch.cuda.device(self.device):
+            C.check(self._L.gf_guidance_batch_host(_ptr_array(scenes_host), self._Ns, self.B, self.Q, self.k,
+                                                   ctypes.c_float(self.radius), self.max_step, self._seeds_p,
+                                                   self._geo_p, C.ptr(self._ws), self._nbytes,
+                                                   ctypes.c_void_p(self.stream.cuda_stream)), "guidance_batch_host")
+        return self.seeds_host, self.geo_host

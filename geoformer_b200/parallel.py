@@ -179,14 +179,40 @@ def seed_sharded_guidance_fused(xyz, n_queries, neighbor, radius, max_step, rows
     return seeds, rows.geo
 
 
+def _guidance_shard(xyz, n_queries, q0, q1, neighbor, radius, max_step):
+    """one library call: FPS of all seeds next to the kNN graph, then this rank's block of seeds (gf_guidance_shard)"""
+    import ctypes
+
+    from . import _capi as C
+
+    C.check_cuda_f32(xyz, "xyz")
+    N, dev = xyz.shape[0], xyz.device
+    seeds = torch.empty((n_queries,), dtype=torch.int32, device=dev)
+    block = torch.empty((q1 - q0, N), dtype=torch.float32, device=dev)
+    L = C.lib()
+    with torch.cuda.device(dev):
+        nbytes = L.gf_guidance_workspace_bytes(N, n_queries, int(neighbor))
+        ws = C.workspace.get(dev, "guidance", nbytes)
+        C.check(L.gf_guidance_shard(C.ptr(xyz), N, n_queries, q0, q1, int(neighbor), ctypes.c_float(float(radius)),
+                                    int(max_step), C.ptr(seeds), C.ptr(block), None, None, C.ptr(ws), nbytes,
+                                    C.stream_of(dev)), "guidance_shard")
+    return seeds, block
+
+
 def seed_sharded_guidance(xyz, n_queries, neighbor, radius, max_step, group=None, fps_fn=None, geodesic_fn=None,
                           gather=True):
     """One scene split by seed blocks.  Returns (seeds (Q,), geo): geo is the full (Q, N) matrix on
-    every rank when gather=True, else this rank's (Q_local, N) block."""
+    every rank when gather=True, else this rank's (Q_local, N) block.
+    gather=False is the mode that SCALES: nothing is exchanged, so the consumer of the maps (the decoder's bias
+    epilogue, the mask head) has to be sharded by query as well -- each of those is row-wise in the queries.
+    Replicating the 2 GB result of a 1M-point scene on every rank costs more than the propagation it follows."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    seeds = (fps_fn or _default_fps)(xyz, n_queries)
     q0, q1 = shard_seeds(n_queries, rank, world)
-    local = (geodesic_fn or _default_geodesic)(xyz, seeds[q0:q1].contiguous(), neighbor, radius, max_step)
+    if fps_fn is None and geodesic_fn is None and xyz.is_cuda:
+        seeds, local = _guidance_shard(xyz, n_queries, q0, q1, neighbor, radius, max_step)
+    else:
+        seeds = (fps_fn or _default_fps)(xyz, n_queries)
+        local = (geodesic_fn or _default_geodesic)(xyz, seeds[q0:q1].contiguous(), neighbor, radius, max_step)
     if not gather or world == 1:
         return seeds, local
     N = xyz.shape[0]

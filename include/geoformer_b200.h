@@ -172,6 +172,12 @@ int gf_guidance_batch(const float *const *xyz, const int *Ns, int B, int Q, int 
  * addresses of the peers' matrices in this process come from gf_peer_open).  n_peers <= 15.  The
  * caller separates consecutive calls by a barrier among the ranks (before: peers finished reading
  * the previous result; after: all rows have landed).                                              */
+/* The same partition without any exchange: FPS samples all Q seeds (replicated: it is sequential and cheap next to
+ * the propagation of a large scene), this rank propagates the seeds [q0, q1) into geo_block (q1 - q0, N); the
+ * consumer of the maps is then sharded by query as well.  Workspace: gf_guidance_workspace_bytes(N, Q, k).       */
+int gf_guidance_shard(const float *xyz, int N, int Q, int q0, int q1, int k, float radius, int max_step, int *seeds,
+                      float *geo_block, int64_t *stats, float *row_max_block, void *workspace,
+                      size_t workspace_bytes, void *stream);
 int gf_geodesic_scatter(const float *knn_dist, const void *knn_idx, int idx_is_i64, int N, int k, const int *seeds,
                         int Q, float radius, int max_step, float *geo, float *const *peer_geo, int n_peers,
                         int64_t *stats, void *workspace, size_t workspace_bytes, void *stream);
@@ -193,6 +199,15 @@ int gf_peer_close(void *dev_ptr);
 size_t gf_guidance_host_workspace_bytes(int N, int Q, int k);
 int gf_guidance_host(const float *xyz_host, int N, int Q, int k, float radius, int max_step, int *seeds_host,
                      float *geo_host, void *workspace, size_t workspace_bytes, void *stream);
+
+/* The batched call with HOST buffers: xyz_host[b] (Ns[b],3) in, seeds_host[b] (Q) and geo_host[b] (Q,Ns[b]) out
+ * (pinned memory for full copy speed); the pointer arrays live in host memory too.  Copies are issued on
+ * `stream`, the call returns after the results are in host memory.  Two callers on two streams keep the link
+ * busy: the device -> host copy of one batch (the maps are 4*Q*N bytes per scene) runs under the next batch.  */
+size_t gf_guidance_batch_host_workspace_bytes(const int *Ns, int B, int Q, int k);
+int gf_guidance_batch_host(const float *const *xyz_host, const int *Ns, int B, int Q, int k, float radius,
+                           int max_step, int *const *seeds_host, float *const *geo_host, void *workspace,
+                           size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

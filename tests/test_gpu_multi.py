@@ -36,6 +36,13 @@ def _worker(rank, world, port, out_dir):
             ref_seeds, ref_geo = geodesic_guidance(x, Q, 16, 0.5, 24)
             assert torch.equal(seeds, ref_seeds)
             assert geo.shape == (Q, 60_000) and torch.equal(geo, ref_geo)
+            # no exchange (gf_guidance_shard: FPS of all seeds, this rank's block of rows only)
+            from geoformer_b200.parallel import shard_seeds
+
+            seeds_b, block = seed_sharded_guidance(x, Q, 16, 0.5, 24, gather=False)
+            q0, q1 = shard_seeds(Q, rank, world)
+            assert torch.equal(seeds_b, ref_seeds) and block.shape == (q1 - q0, 60_000)
+            assert torch.equal(block, ref_geo[q0:q1])
         # exchange fused into the propagation kernel (rows stored into the peers' matrices over NVLink)
         from geoformer_b200.parallel import SeedShardedRows, seed_sharded_guidance_fused
 

@@ -567,6 +567,20 @@ def test_batch_guidance_runner_graph_and_stage_events(dev):
         r.close()
 
 
+def test_batch_host_entry_point_equals_device_path(dev):
+    """gf_guidance_batch_host: pinned host points in, seeds + maps back in pinned host memory == the device path"""
+    from geoformer_b200.guidance import HostBatchGuidance, geodesic_guidance
+
+    N, B, Q, k = 25000, 3, 32, 16
+    xs = [scene(N, 80 + i) for i in range(B)]
+    h = HostBatchGuidance(N, B, Q, k, 0.5, 18, device=dev)
+    for rep in range(2):
+        seeds, geo = h.run([x.pin_memory() for x in xs])
+        for b, x in enumerate(xs):
+            rs, rg = geodesic_guidance(x.to(dev), Q, k, 0.5, 18)
+            assert torch.equal(seeds[b], rs.cpu()) and torch.equal(geo[b], rg.cpu()), (rep, b)
+
+
 def test_row_max_by_product(oracle_lib, dev):
     """The propagation can hand out the maximum of every row (what both epilogues start from); it must be
     exactly geo.max(dim=1), also for rows that stay empty, and the mask-head epilogue fed with it must
