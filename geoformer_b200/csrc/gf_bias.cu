@@ -229,6 +229,25 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ordered-uint row maxima of the gathered maps and their global maximum (geoformer_fs.py:685-692); geo_ptrs / geo_ld
+// are HOST arrays of B device pointers / row strides.  Shared with the fused cross-attention (gf_attention.cu).
+int bias_ctx_rowmax(const float *const *geo_ptrs, const int *geo_ld, const int *ctx_idx, int B, int Q, int C,
+                    uint32_t *rowmax, uint32_t *gmax, cudaStream_t st) {
+  if (gmax != rowmax + (size_t)B * Q) {
+    set_error("bias: the global maximum must follow the row maxima (they are cleared together)");
+    return GF_ERR_INVALID;
+  }
+  bias_zero_kernel<<<(B * Q + 256) / 256, 256, 0, st>>>(rowmax, B * Q + 1);
+  GF_LAUNCHED();
+  const int rchunks = C >= 1024 ? 4 : 1;
+  for (int b = 0; b < B; ++b) {
+    bias_ctx_rowmax_kernel<<<dim3(rchunks, Q), 256, 0, st>>>(geo_ptrs[b], geo_ld[b], ctx_idx + (size_t)b * C, C,
+                                                           rowmax + (size_t)b * Q, gmax);
+    GF_LAUNCHED();
+  }
+  return GF_OK;
+}
+
 }  // namespace gf
 
 using namespace gf;

@@ -137,6 +137,27 @@ int gf_bias_decoder_fourier(const float *const *geo_ptrs, const int *geo_ld, con
 int gf_bias_mask_head(const float *geo, const float *coords, const float *seed_xyz, int Q, int N,
                       const float *row_max, float *out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- the consumer of the decoder bias: vector cross-attention -----------------------------
+ * model/transformer_detr.py:443-454 (MLPs :384-396): for every query q and context c
+ *     sim = W2 relu(W1 (tgt2[q] - memory[c] + rel[q,c]) + b1) + b2,   v2 = Wv (memory[c] + rel[q,c]) + bv
+ *     out[q] = relu(Wo (sum_c softmax_c(sim / 8) * v2) + bo)          (softmax over the contexts, per channel)
+ * tgt2 (Q,B,64) = norm2(tgt), memory (C,B,64), relative_pos (Q,C,B,64), weights (64,64) row-major (out,in) like
+ * nn.Linear.weight -> out (Q,B,64), all f32 device.  One tcgen05 kernel (TF32 products, fp32 accumulation in
+ * TMEM); the three (Q,C,B,64) temporaries of the reference are never materialised.  Tolerance vs fp32: 2e-3.
+ * The _fused variant takes the arguments of gf_bias_decoder_fourier instead of relative_pos and builds the
+ * embedding tile by tile in shared memory (32 frequencies: channels [sin | cos], B <= 8).                    */
+size_t gf_rel_cross_attention_workspace_bytes(int Q, int C, int B);
+int gf_rel_cross_attention(const float *tgt2, const float *memory, const float *relative_pos, int Q, int C, int B,
+                           const float *w1, const float *b1, const float *w2, const float *b2, const float *wv,
+                           const float *bv, const float *wo, const float *bo, float *out, void *workspace,
+                           size_t workspace_bytes, void *stream);
+int gf_rel_cross_attention_fused(const float *tgt2, const float *memory, const float *const *geo_ptrs,
+                                 const int *geo_ld, const int *ctx_idx, const float *query_xyz, const float *ctx_xyz,
+                                 const float *gauss_B, int gauss_ld, const float *pc_min, const float *pc_max, int Q,
+                                 int C, int B, const float *w1, const float *b1, const float *w2, const float *b2,
+                                 const float *wv, const float *bv, const float *wo, const float *bo, float *out,
+                                 void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- fused hot path: FPS -> kNN -> geodesic -------------------------------------------------- */
 
 /* Device-resident scene: xyz (N,3) -> seeds (Q) i32, geo (Q,N) f32.  knn_dist / knn_idx32 (N,k)

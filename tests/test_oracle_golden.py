@@ -237,3 +237,19 @@ def test_bias_fixture_is_what_the_reference_lines_produce_today():
         out = dec_fn([T(g["d%d_geo%d" % (i, b)]) for b in range(B)], T(g["d%d_inds" % i]), T(g["d%d_qry" % i]),
                      T(g["d%d_ctx" % i]))
         assert np.array_equal(out.numpy(), g["d%d_out" % i], equal_nan=True)
+
+
+def test_attention_oracle_matches_reference_layer_fixture():
+    """oracle/attention.py against tests/golden/attention_golden.npz = what the reference's OWN
+    TransformerDecoderLayer.forward_pre_rel computes in its cross-attention block (transformer_detr.py:443-454),
+    captured by forward hooks (tests/golden/make_golden_attention.py).  Same fp32 torch ops: 1e-6."""
+    import torch
+
+    from oracle import attention as oatt
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "attention_golden.npz"))
+    T = lambda a: torch.from_numpy(np.array(a))  # noqa: E731
+    for i in range(int(g["n"])):
+        w = {k: T(g["c%d_%s" % (i, k)]) for k in ("w1", "b1", "w2", "b2", "wv", "bv", "wo", "bo")}
+        out = oatt.rel_cross_attention(T(g["c%d_tgt2" % i]), T(g["c%d_memory" % i]), T(g["c%d_rel" % i]), w)
+        np.testing.assert_allclose(out.numpy(), g["c%d_out" % i], rtol=1e-5, atol=1e-6)
