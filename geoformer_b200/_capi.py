@@ -145,19 +145,27 @@ def check_cuda_i32(x, name):
 
 
 class Workspace:
-    """Grow-only scratch buffers, one per (device, tag); kept alive so async kernels stay valid."""
+    """Grow-only scratch buffers, one per (device, tag, CUDA stream, host thread): two streams or two threads that
+    call the same operator never share scratch (the whole-GPU FPS keeps polled tag slots there, the propagation its
+    claim arrays).  A buffer that is outgrown is kept alive (kernels launched earlier may still be using it)."""
 
     def __init__(self):
         self._bufs = {}
+        self._retired = []
+        self._lock = threading.Lock()
 
     def get(self, device, tag, nbytes):
         nbytes = int(nbytes)
-        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
-        buf = self._bufs.get(key)
-        if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
-            self._bufs[key] = buf
-        return buf
+        dev = device.index if device.index is not None else torch.cuda.current_device()
+        key = (dev, tag, stream_of(device), threading.get_ident())
+        with self._lock:
+            buf = self._bufs.get(key)
+            if buf is None or buf.numel() < nbytes:
+                if buf is not None:
+                    self._retired.append(buf)
+                buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+                self._bufs[key] = buf
+            return buf
 
 
 workspace = Workspace()

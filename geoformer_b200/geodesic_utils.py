@@ -20,6 +20,7 @@ class FlatL2Index:
     def __init__(self, algo="grid"):
         self.algo = {"grid": 0, "brute": 1}[algo]
         self._x = None
+        self._src = None
 
     @property
     def ntotal(self):
@@ -28,10 +29,13 @@ class FlatL2Index:
     def add(self, x):
         C.check_cuda_f32(x, "x")
         C.require(x.dim() == 2 and x.size(1) == 3, "x must be (N, 3)")
-        self._x = x if self._x is None else torch.cat([self._x, x]).contiguous()
+        # faiss copies what it is given: later changes of the caller's tensor must not change the index
+        self._x = x.detach().clone() if self._x is None else torch.cat([self._x, x]).contiguous()
+        self._src = (x.data_ptr(), tuple(x.shape)) if self.ntotal == x.size(0) else None
 
     def reset(self):
         self._x = None
+        self._src = None
 
     def search(self, q, k, D_out, I_out):
         C.require(self._x is not None, "search on an empty index")
@@ -41,7 +45,9 @@ class FlatL2Index:
         nq = q.size(0)
         C.require(tuple(D_out.shape) == (nq, k) and tuple(I_out.shape) == (nq, k), "output shape must be (nq, k)")
         x = self._x
-        same = q.data_ptr() == x.data_ptr() and q.shape == x.shape
+        # the reference searches a scene against itself right after adding it (geodesic_utils.py:18-19): then the
+        # self-query path (no second copy of the points) applies
+        same = self._src == (q.data_ptr(), tuple(q.shape))
         _knn_into(x, None if same else q, int(k), False, D_out, I_out, None, self.algo)
         return D_out, I_out
 
@@ -76,6 +82,11 @@ def find_knn(gpu_index, locs, neighbor=32):
     """geodesic_utils.py:11-24: (sqrt distances (N,k) f32, indices (N,k) i64) through the index
     protocol.  With our own FlatL2Index the sqrt is fused into the search kernel."""
     if isinstance(gpu_index, FlatL2Index) or gpu_index is None:
+        # the reference adds the scene, searches it against itself and resets the index (:18-21): points added
+        # earlier would take part in the search, so an index that is not empty is an error here, not ignored
+        C.require(gpu_index is None or gpu_index.ntotal == 0,
+                  "find_knn: the index already holds %d points (the reference resets it after every call)"
+                  % (0 if gpu_index is None else gpu_index.ntotal))
         algo = "grid" if gpu_index is None or gpu_index.algo == 0 else "brute"
         return knn_graph(locs.contiguous(), neighbor, algo=algo)
     n_points = locs.shape[0]

@@ -243,6 +243,42 @@ def test_flat_index_protocol(oracle_lib, dev):
     assert np.array_equal(Ik.cpu().numpy(), rI) and np.array_equal(Dk.cpu().numpy(), rD)
 
 
+def test_flat_index_copies_its_points_and_streams_do_not_share_scratch(dev):
+    """faiss copies on add(): mutating the caller's tensor afterwards must not change the index; find_knn refuses an
+    index that still holds points (the reference resets it after every call).  Two streams running the hot path at
+    the same time get scratch of their own (Workspace is keyed by stream and thread)."""
+    from geoformer_b200.geodesic_utils import FlatL2Index, find_knn, knn_graph
+    from geoformer_b200.guidance import geodesic_guidance
+
+    x = scene(6000, 5).to(dev)
+    keep = x.clone()
+    index = FlatL2Index()
+    index.add(x)
+    x.mul_(3.0)  # the caller's tensor changes after add()
+    D = torch.zeros(6000, 8, device=dev)
+    I = torch.zeros(6000, 8, dtype=torch.int64, device=dev)
+    index.search(keep, 8, D, I)
+    rD, rI = knn_graph(keep, 8)
+    assert torch.equal(I, rI) and torch.equal(torch.sqrt(D), rD)
+    with pytest.raises(RuntimeError):
+        find_knn(index, keep, neighbor=8)
+    index.reset()
+    Dk, Ik = find_knn(index, keep, neighbor=8)
+    assert torch.equal(Ik, rI) and torch.equal(Dk, rD)
+    xa, xb = scene(30000, 6).to(dev), scene(45000, 7).to(dev)
+    want_a, want_b = geodesic_guidance(xa, 40, 16, 0.5, 20), geodesic_guidance(xb, 40, 16, 0.5, 20)
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    for _ in range(4):
+        with torch.cuda.stream(sa):
+            ga = geodesic_guidance(xa, 40, 16, 0.5, 20)
+        with torch.cuda.stream(sb):
+            gb = geodesic_guidance(xb, 40, 16, 0.5, 20)
+        torch.cuda.synchronize()
+        assert torch.equal(ga[0], want_a[0]) and torch.equal(ga[1], want_a[1])
+        assert torch.equal(gb[0], want_b[0]) and torch.equal(gb[1], want_b[1])
+
+
 def test_knn_grid_equals_brute_at_full_size(dev):
     """c2 size (too slow for the CPU oracle in a unit test): the two GPU algorithms must agree."""
     from geoformer_b200.geodesic_utils import knn_graph
