@@ -26,12 +26,15 @@
 namespace gf {
 
 constexpr int ATT_D = 64;        // channels (dec_dim of the model, geoformer_fs.py:116)
-constexpr int ATT_TILE = 128;    // contexts per tile = MMA N
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_TILE = 64;     // contexts per tile = MMA N
+constexpr int ATT_THREADS = 256;
 constexpr int ATT_MAX_B = 8;     // batch elements of the fused variant (map pointers travel in the kernel parameters)
-constexpr int ATT_HALF_BYTES = ATT_TILE * 128;  // one K-half (32 floats = 128 bytes per row) of a 128-row tile
-constexpr int ATT_TILE_BYTES = 2 * ATT_HALF_BYTES;
-constexpr int ATT_SMEM = 4 * ATT_TILE_BYTES + 1024;  // A1, A2, embedding tile, hidden tile (+ alignment slack)
+constexpr int ATT_W_HALF = 128 * 128;           // one K-half (32 floats = 128 bytes per row) of a 128-row weight tile
+constexpr int ATT_W_BYTES = 2 * ATT_W_HALF;     // [Wv; W1] and [W2; 0]: 128 x 64 fp32
+constexpr int ATT_T_HALF = ATT_TILE * 128;      // one K-half of a 64-row operand tile (embedding / hidden)
+constexpr int ATT_T_BYTES = 2 * ATT_T_HALF;
+constexpr int ATT_SMEM = 2 * ATT_W_BYTES + 4 * ATT_T_BYTES + 1024;  // A1, A2, 2 embedding tiles, 2 hidden tiles
+constexpr uint32_t ATT_D1_COL = 0, ATT_D2_COL = 3 * ATT_TILE;       // TMEM: three D1 buffers, two D2 buffers
 
 struct AttArgs {
   const float *aq;   // (B, Q, 64)  W1 tgt2[q] + b1
@@ -56,10 +59,11 @@ struct AttArgs {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// K-major tile with 128-byte swizzle: row r, fp32 column k (0..63) -> byte offset inside the tile
+// K-major tile with 128-byte swizzle, `rows` rows: row r, fp32 column k (0..63) -> byte offset inside the tile
+template <int ROWS>
 __device__ __forceinline__ uint32_t sw128_off(int r, int k) {
   const int half = k >> 5, kk = k & 31;
-  return (uint32_t)(half * ATT_HALF_BYTES + r * 128 + ((((kk >> 2) ^ (r & 7)) << 4) | ((kk & 3) << 2)));
+  return (uint32_t)(half * (ROWS * 128) + r * 128 + ((((kk >> 2) ^ (r & 7)) << 4) | ((kk & 3) << 2)));
 }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
@@ -67,7 +71,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = 128
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = 64
 constexpr uint32_t ATT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((ATT_TILE >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
@@ -79,14 +83,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       : "memory");
 }
 
-// D (128 x 128, TMEM) = A (128 x 64) * B^T (128 x 64): eight K = 8 steps, 32 bytes apart inside a swizzled row,
-// the second half of K in the second half-tile
-__device__ __forceinline__ void umma_tile(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr) {
+// D (128 x 64, TMEM) = A (128 x 64) * B^T (64 x 64): eight K = 8 steps, 32 bytes apart inside a swizzled row, the
+// second half of K in the second half-tile; then the completion of everything issued so far arrives on `mbar`
+__device__ __forceinline__ void umma_tile(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr, uint32_t mbar) {
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
-    const uint32_t koff = (uint32_t)((kk >> 2) * ATT_HALF_BYTES + (kk & 3) * 32);
-    umma_tf32(d_tmem, umma_desc(a_saddr + koff), umma_desc(b_saddr + koff), kk > 0);
+    const uint32_t ka = (uint32_t)((kk >> 2) * ATT_W_HALF + (kk & 3) * 32), kb = (uint32_t)((kk >> 2) * ATT_T_HALF + (kk & 3) * 32);
+    umma_tf32(d_tmem, umma_desc(a_saddr + ka), umma_desc(b_saddr + kb), kk > 0);
   }
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
@@ -115,47 +120,59 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Software pipeline over the tiles of one (query, batch element), one __syncthreads per tile.  In iteration i
+//   every thread    loads tile i+2 of the embedding into the operand buffer tile i has just released
+//   warps 2,3,6,7   (TMEM lanes 64..127) turn product 1 of tile i into the hidden tile  (two warps per lane
+//                   quadrant, 32 contexts each)
+//   warps 0,1,4,5   (TMEM lanes 0..63) run softmax + weighted sum of tile i-1 from product 2 and the v2 rows of product 1
+//   thread 0        then issues product 2 of tile i and product 1 of tile i+2; both complete under the next iteration.
+// Product 1 of a tile is issued two iterations before it is consumed, product 2 one iteration: three D1 and two D2
+// accumulator buffers in TMEM, one mbarrier per buffer.
 template <bool FUSED>
 __global__ void __launch_bounds__(ATT_THREADS, 1) rel_cross_attention_kernel(const AttArgs a) {
   extern __shared__ unsigned char att_smem_raw[];
-  __shared__ __align__(8) unsigned long long s_mbar[2];
+  __shared__ __align__(8) unsigned long long s_mbar[5];  // [0..2] product 1 into D1[b], [3..4] product 2 into D2[b]
   __shared__ uint32_t s_tmem;
+  __shared__ float s_part[3][2][ATT_D];  // partial softmax states (max, sum, weighted sum) of the two column halves
   __shared__ float s_out[ATT_D];
-  const unsigned tid = threadIdx.x, warp = tid >> 5;
+  const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
   const int q = blockIdx.x, b = blockIdx.y;
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char *sA1 = smem, *sA2 = smem + ATT_TILE_BYTES, *sR = smem + 2 * ATT_TILE_BYTES, *sH = smem + 3 * ATT_TILE_BYTES;
-  const uint32_t mbar0 = smem_u32(&s_mbar[0]), mbar1 = smem_u32(&s_mbar[1]);
+  unsigned char *sA1 = smem, *sA2 = smem + ATT_W_BYTES, *sR = smem + 2 * ATT_W_BYTES, *sH = sR + 2 * ATT_T_BYTES;
+  uint32_t mbar[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) mbar[i] = smem_u32(&s_mbar[i]);
 
   // ---- one-time set-up: weights into swizzled K-major tiles, TMEM, barriers -----------------------------------
   // A1 rows 0..63 = Wv, rows 64..127 = W1;  A2 rows 0..63 = W2, rows 64..127 = 0
   for (int e = tid; e < 128 * ATT_D; e += ATT_THREADS) {
     const int r = e >> 6, k = e & 63;
-    *reinterpret_cast<float *>(sA1 + sw128_off(r, k)) = r < 64 ? __ldg(a.wv + r * 64 + k) : __ldg(a.w1 + (r - 64) * 64 + k);
-    *reinterpret_cast<float *>(sA2 + sw128_off(r, k)) = r < 64 ? __ldg(a.w2 + r * 64 + k) : 0.f;
+    *reinterpret_cast<float *>(sA1 + sw128_off<128>(r, k)) = r < 64 ? __ldg(a.wv + r * 64 + k) : __ldg(a.w1 + (r - 64) * 64 + k);
+    *reinterpret_cast<float *>(sA2 + sw128_off<128>(r, k)) = r < 64 ? __ldg(a.w2 + r * 64 + k) : 0.f;
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&s_tmem)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar1) : "memory");
+#pragma unroll
+    for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar[i]) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the weight tiles were written through the generic proxy
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = s_tmem;
-  const uint32_t t_lane = tmem + ((warp * 32u) << 16);  // this warp's 32 TMEM lanes
 
-  // per-thread constants: threads 0..63 own output channel f = tid (v2, sim); threads 64..127 hidden channel i
-  const int ch = tid & 63;
-  const float aq = tid >= 64 ? __ldg(a.aq + ((size_t)b * a.Q + q) * 64 + ch) : 0.f;
-  const float b2 = tid < 64 ? __ldg(a.b2 + ch) : 0.f;
+  // roles and per-thread constants
+  const bool hidden_role = (warp & 2u) != 0;     // warps 2,3,6,7: TMEM lanes 64..127
+  const int ch = (int)(((warp & 1u) << 5) | lane);  // channel inside the role's 64 lanes
+  const int colhalf = (int)(warp >> 2) * 32;      // which 32 of the tile's 64 contexts this warp handles
+  const float aq = hidden_role ? __ldg(a.aq + ((size_t)b * a.Q + q) * 64 + ch) : 0.f;
+  const float b2 = hidden_role ? 0.f : __ldg(a.b2 + ch);
   const float *p1 = a.p1 + (size_t)b * a.C * 64, *pv = a.pv + (size_t)b * a.C * 64;
-  float m_run = -INFINITY, s_run = 0.f, acc = 0.f;  // online softmax over the contexts, per channel
+  // hidden-tile store addresses: half-tile and word of column ch, plus the eight swizzled chunk offsets
+  const uint32_t h_base = (uint32_t)((ch >> 5) * ATT_T_HALF + colhalf * 128 + ((ch & 3) << 2));
+  uint32_t h_sw[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h_sw[j] = (uint32_t)((((ch & 31) >> 2) ^ j) << 4);
+  float m_run = -INFINITY, s_run = 0.f, acc = 0.f;  // online softmax over this warp's contexts, per channel
 
   // ingredients of the fused embedding (gf_bias.cu: bias_ctx_fourier_kernel)
   float fm = 0.f, qx = 0.f, qy = 0.f, qz = 0.f, mn0 = 0.f, mn1 = 0.f, mn2 = 0.f, df0 = 1.f, df1 = 1.f, df2 = 1.f;
@@ -171,120 +188,177 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) rel_cross_attention_kernel(con
     geo_row = a.geo[b] + (size_t)q * a.geo_ld[b];
   }
 
-  const int ntiles = (a.C + ATT_TILE - 1) / ATT_TILE;
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const int c0 = tile * ATT_TILE;
-    const uint32_t parity = (uint32_t)(tile & 1);
-    // ---- the embedding tile: thread t writes row t (context c0 + t), 64 fp32, swizzled ------------------------
-    {
-      const int c = c0 + (int)tid;
-      if (!FUSED) {
-        const float4 *src = reinterpret_cast<const float4 *>(a.rel + (((size_t)q * a.C + (c < a.C ? c : 0)) * a.B + b) * 64);
+  // The embedding tile in two steps, so that its global loads are in flight while the thread does its role's work:
+  // fetch(tile) issues them (a quarter of row t / 4: 16 floats, or for the fused variant the gathered map entry and the
+  // context's coordinates), stash(buf) writes the operand buffer (fused: after the sin / cos of its eight frequencies).
+  float4 pre[4];
+  float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+  bool pre_live = false;
+  const int lr = (int)(tid >> 2), qd = (int)(tid & 3u);
+  // shared-space addresses with the swizzle folded into per-thread constants: no address arithmetic per store
+  const uint32_t sR_s = smem_u32(sR), sH_s = smem_u32(sH);
+  uint32_t st_off[4];  // this thread's four 16-byte chunks of row lr (unfused: columns 16 qd + 4 j; fused: see stash)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 v = c < a.C ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4 *>(sR + sw128_off((int)tid, 4 * j)) = v;
-        }
-      } else {
-        float n0 = 0.f, n1 = 0.f, n2 = 0.f;
-        if (c < a.C) {
-          const float g = __ldg(geo_row + __ldg(a.ctx_idx + (size_t)b * a.C + c));
-          float v0 = g, v1 = g, v2 = g;
-          if (g < 0.f) {  // :699-702
-            const float *cx = a.ctx_xyz + ((size_t)b * a.C + c) * 3;
-            v0 = __fadd_rn(fm, fabsf(__fsub_rn(qx, cx[0])));
-            v1 = __fadd_rn(fm, fabsf(__fsub_rn(qy, cx[1])));
-            v2 = __fadd_rn(fm, fabsf(__fsub_rn(qz, cx[2])));
-          }
-          const float two_pi = 6.2831855f;
-          n0 = __fmul_rn(__fdiv_rn(__fsub_rn(v0, mn0), df0), two_pi);
-          n1 = __fmul_rn(__fdiv_rn(__fsub_rn(v1, mn1), df1), two_pi);
-          n2 = __fmul_rn(__fdiv_rn(__fsub_rn(v2, mn2), df2), two_pi);
-        }
+  for (int j = 0; j < 4; ++j)
+    st_off[j] = FUSED ? sw128_off<ATT_TILE>(lr, (j & 1) * 32 + 8 * qd + 4 * (j >> 1)) : sw128_off<ATT_TILE>(lr, 16 * qd + 4 * j);
+  auto sts128 = [](uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  };
+  auto fetch = [&](int tile) {
+    const int c = tile * ATT_TILE + lr;
+    pre_live = c < a.C;
+    if (!FUSED) {
+      const float4 *src = reinterpret_cast<const float4 *>(a.rel + (((size_t)q * a.C + (pre_live ? c : 0)) * a.B + b) * 64) + 4 * qd;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {  // four frequencies at a time: sin -> columns j, cos -> columns 32 + j
-          float sn[4], cs[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = 4 * j4 + e;
-            const float p = fmaf(n2, __ldg(a.gauss_B + 2 * a.ldb + j), fmaf(n1, __ldg(a.gauss_B + a.ldb + j), __fmul_rn(n0, __ldg(a.gauss_B + j))));
-            sincosf(p, &sn[e], &cs[e]);
-            if (c >= a.C) sn[e] = cs[e] = 0.f;
-          }
-          *reinterpret_cast<float4 *>(sR + sw128_off((int)tid, 4 * j4)) = make_float4(sn[0], sn[1], sn[2], sn[3]);
-          *reinterpret_cast<float4 *>(sR + sw128_off((int)tid, 32 + 4 * j4)) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+      for (int j = 0; j < 4; ++j) pre[j] = pre_live ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      n0 = n1 = n2 = 0.f;
+      if (pre_live) {
+        const float g = __ldg(geo_row + __ldg(a.ctx_idx + (size_t)b * a.C + c));
+        float v0 = g, v1 = g, v2 = g;
+        if (g < 0.f) {  // :699-702
+          const float *cx = a.ctx_xyz + ((size_t)b * a.C + c) * 3;
+          v0 = __fadd_rn(fm, fabsf(__fsub_rn(qx, cx[0])));
+          v1 = __fadd_rn(fm, fabsf(__fsub_rn(qy, cx[1])));
+          v2 = __fadd_rn(fm, fabsf(__fsub_rn(qz, cx[2])));
         }
+        const float two_pi = 6.2831855f;
+        n0 = __fmul_rn(__fdiv_rn(__fsub_rn(v0, mn0), df0), two_pi);
+        n1 = __fmul_rn(__fdiv_rn(__fsub_rn(v1, mn1), df1), two_pi);
+        n2 = __fmul_rn(__fdiv_rn(__fsub_rn(v2, mn2), df2), two_pi);
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();  // tile complete; every thread has finished reading the previous tile's accumulators
-    // ---- product 1: lanes 0..63 <- Wv rel, lanes 64..127 <- W1 rel (TMEM columns 0..127) ----------------------
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      umma_tile(tmem, smem_u32(sA1), smem_u32(sR));
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar0) : "memory");
+  };
+  auto stash = [&](int buf) {
+    const uint32_t dst = sR_s + (uint32_t)buf * ATT_T_BYTES;
+    if (!FUSED) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sts128(dst + st_off[j], pre[j]);
+    } else {
+#pragma unroll
+      for (int j4 = 0; j4 < 2; ++j4) {  // this thread's eight frequencies: sin -> columns j, cos -> columns 32 + j
+        float sn[4], cs[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 8 * qd + 4 * j4 + e;
+          const float p = fmaf(n2, __ldg(a.gauss_B + 2 * a.ldb + j), fmaf(n1, __ldg(a.gauss_B + a.ldb + j), __fmul_rn(n0, __ldg(a.gauss_B + j))));
+          sincosf(p, &sn[e], &cs[e]);
+          if (!pre_live) sn[e] = cs[e] = 0.f;
+        }
+        sts128(dst + st_off[2 * j4], make_float4(sn[0], sn[1], sn[2], sn[3]));
+        sts128(dst + st_off[2 * j4 + 1], make_float4(cs[0], cs[1], cs[2], cs[3]));
+      }
     }
-    mbar_wait(mbar0, parity);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- hidden layer (threads 64..127): h = relu(W1 rel + W1 tgt2[q] + b1 - W1 memory[c]) -> hidden tile --------
-    if (tid >= 64) {
-#pragma unroll 1
-      for (int cc = 0; cc < ATT_TILE; cc += 32) {
+  };
+  auto load_tile = [&](int tile, int buf) {
+    fetch(tile);
+    stash(buf);
+  };
+
+  const int T = (a.C + ATT_TILE - 1) / ATT_TILE;
+  load_tile(0, 0);
+  if (T > 1) load_tile(1, 1);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // tiles were written through the generic proxy
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  const uint32_t t_lane = tmem + (((warp & 3u) * 32u) << 16);  // this warp's 32 TMEM lanes
+  if (tid == 0) {
+    umma_tile(tmem + ATT_D1_COL, smem_u32(sA1), smem_u32(sR), mbar[0]);
+    if (T > 1) umma_tile(tmem + ATT_D1_COL + ATT_TILE, smem_u32(sA1), smem_u32(sR + ATT_T_BYTES), mbar[1]);
+  }
+
+  for (int i = 0; i <= T; ++i) {
+    // global loads first: tile i + 2 of the embedding and this thread's 32 table entries of the tile it works on
+    const bool more = i + 2 < T;
+    if (more) fetch(i + 2);
+    float tab[32];
+    {
+      const int t = hidden_role ? i : i - 1;
+      const float *src = (hidden_role ? p1 : pv) + ch;
+      const int c0 = t * ATT_TILE + colhalf;
+      if (t >= 0 && t < T) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) tab[e] = c0 + e < a.C ? __ldg(src + (size_t)(c0 + e) * 64) : 0.f;
+      }
+    }
+    if (i < T) {  // product 1 of tile i has landed in D1[i % 3]; the operand buffer i % 2 is free again
+      mbar_wait(mbar[i % 3], (uint32_t)((i / 3) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (hidden_role) {
+      if (i < T) {  // h = relu(W1 rel + (W1 tgt2[q] + b1) - W1 memory[c]) -> hidden tile i % 2, row = context, column = ch
         float d[32];
-        tmem_ld32(t_lane + (uint32_t)cc, d);
+        tmem_ld32(t_lane + ATT_D1_COL + (uint32_t)((i % 3) * ATT_TILE + colhalf), d);
+        // row colhalf + e, column ch: (colhalf + e) & 7 == e & 7, so the swizzled chunk is one of eight per-thread
+        // constants and the row is an immediate offset
+        const uint32_t dst = sH_s + (uint32_t)(i & 1) * ATT_T_BYTES + h_base;
+        const int c0 = i * ATT_TILE + colhalf;
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          const int c = c0 + cc + e;
-          const float h = c < a.C ? fmaxf(d[e] + aq - __ldg(p1 + (size_t)c * 64 + ch), 0.f) : 0.f;
-          *reinterpret_cast<float *>(sH + sw128_off(cc + e, ch)) = h;
+          const float h = c0 + e < a.C ? fmaxf(d[e] + aq - tab[e], 0.f) : 0.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + h_sw[e & 7] + (uint32_t)e * 128u), "f"(h) : "memory");
         }
       }
+    } else if (i >= 1) {  // softmax over the contexts and weighted sum of tile i - 1
+      const int t = i - 1;
+      mbar_wait(mbar[3 + (t & 1)], (uint32_t)((t >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float sv[32], vv[32];
+      tmem_ld32(t_lane + ATT_D2_COL + (uint32_t)((t & 1) * ATT_TILE + colhalf), sv);
+      tmem_ld32(t_lane + ATT_D1_COL + (uint32_t)((t % 3) * ATT_TILE + colhalf), vv);
+      const int c0 = t * ATT_TILE + colhalf;
+      float mx = m_run;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        sv[e] = c0 + e < a.C ? (sv[e] + b2) * 0.125f : -INFINITY;  // / sqrt(64), :449
+        mx = fmaxf(mx, sv[e]);
+      }
+      if (mx > -INFINITY) {
+        const float scale = __expf(m_run - mx);  // exp(-inf) = 0 for the first contexts
+        s_run *= scale, acc *= scale;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          if (c0 + e < a.C) {
+            const float w = __expf(sv[e] - mx);
+            s_run += w;
+            acc = fmaf(w, vv[e] + tab[e], acc);
+          }
+        }
+        m_run = mx;
+      }
     }
+    if (more) stash(i & 1);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    // ---- product 2: lanes 0..63 <- W2 h (TMEM columns 128..255) ------------------------------------------------
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      umma_tile(tmem + 128u, smem_u32(sA2), smem_u32(sH));
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar1) : "memory");
-    }
-    mbar_wait(mbar1, parity);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- softmax over the contexts and weighted sum (threads 0..63: channel f = tid) ---------------------------
-    if (tid < 64) {
-#pragma unroll 1
-      for (int cc = 0; cc < ATT_TILE; cc += 32) {
-        float sv[32], vv[32];
-        tmem_ld32(t_lane + 128u + (uint32_t)cc, sv);
-        tmem_ld32(t_lane + (uint32_t)cc, vv);
-        float mx = m_run;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          sv[e] = c0 + cc + e < a.C ? (sv[e] + b2) * 0.125f : -INFINITY;  // / sqrt(64), :449
-          mx = fmaxf(mx, sv[e]);
-        }
-        if (mx > -INFINITY) {
-          const float scale = __expf(m_run - mx);  // exp(-inf) = 0 on the first tile
-          s_run *= scale, acc *= scale;
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int c = c0 + cc + e;
-            if (c < a.C) {
-              const float w = __expf(sv[e] - mx);
-              s_run += w;
-              acc = fmaf(w, vv[e] + __ldg(pv + (size_t)c * 64 + ch), acc);
-            }
-          }
-          m_run = mx;
-        }
-      }
+      if (i < T)  // product 2: lanes 0..63 <- W2 h
+        umma_tile(tmem + ATT_D2_COL + (uint32_t)((i & 1) * ATT_TILE), smem_u32(sA2), smem_u32(sH + (i & 1) * ATT_T_BYTES), mbar[3 + (i & 1)]);
+      if (i + 2 < T)  // product 1 of tile i + 2: lanes 0..63 <- Wv rel, lanes 64..127 <- W1 rel
+        umma_tile(tmem + ATT_D1_COL + (uint32_t)(((i + 2) % 3) * ATT_TILE), smem_u32(sA1), smem_u32(sR + (i & 1) * ATT_T_BYTES), mbar[(i + 2) % 3]);
     }
   }
-  // ---- out_mlp: relu(Wo (acc / s) + bo) ---------------------------------------------------------------------------
-  if (tid < 64) s_out[tid] = s_run > 0.f ? acc / s_run : 0.f;
+  // ---- merge the two column halves, then out_mlp: relu(Wo (acc / s) + bo) ----------------------------------------
+  if (!hidden_role) {
+    const int hh = (int)(warp >> 2);
+    s_part[0][hh][ch] = m_run, s_part[1][hh][ch] = s_run, s_part[2][hh][ch] = acc;
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < 64) {
+    const float m0 = s_part[0][0][tid], m1 = s_part[0][1][tid];
+    const float mx = fmaxf(m0, m1);
+    float s = 0.f, av = 0.f;
+    if (mx > -INFINITY) {
+      const float e0 = __expf(m0 - mx), e1 = __expf(m1 - mx);
+      s = s_part[1][0][tid] * e0 + s_part[1][1][tid] * e1;
+      av = s_part[2][0][tid] * e0 + s_part[2][1][tid] * e1;
+    }
+    s_out[tid] = s > 0.f ? av / s : 0.f;
+  }
   __syncthreads();
   if (tid < 64) {
     float o = __ldg(a.bo + tid);
@@ -292,7 +366,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) rel_cross_attention_kernel(con
     for (int f = 0; f < 64; ++f) o = fmaf(__ldg(a.wo + tid * 64 + f), s_out[f], o);
     a.out[((size_t)q * a.B + b) * 64 + tid] = fmaxf(o, 0.f);
   }
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 }  // namespace gf
