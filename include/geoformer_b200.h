@@ -158,6 +158,20 @@ int gf_rel_cross_attention_fused(const float *tgt2, const float *memory, const f
                                  const float *wv, const float *bv, const float *wo, const float *bo, float *out,
                                  void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- set_aggregator.mlp fused with its grouping --------------------------------------------
+ * lib/pointnet2/pointnet2_modules.py:200-249 + QueryAndGroup.forward (pointnet2_utils.py:303-356) + SharedMLP
+ * (pytorch_utils.py:9-32): per centre j and ball-query neighbour s the input [(xyz[idx] - new_xyz[j]) / radius |
+ * features[:, idx]] goes through n_layers x (1x1 conv, batch norm in inference form, ReLU) and is max- or
+ * mean-pooled over the nsample neighbours.  xyz (B,N,3), new_xyz (B,m,3), features (B,C,N) or NULL, idx (B,m,nsample)
+ * i32 (gf_ball_query) -> out (B, widths[n_layers], m).  widths (n_layers+1, host): input channels (3 + C when use_xyz)
+ * and every layer's output channels, each <= 32; weights[l] (widths[l+1], widths[l]) row-major, scales[l] / shifts[l]
+ * (widths[l+1]): y = relu(scale * (W x) + shift), i.e. gamma / sqrt(var + eps) and beta - mean * that (host arrays of
+ * device pointers).  The (B, 3+C, m, nsample) grouped tensors and per-layer activations are never materialised.   */
+int gf_group_mlp_pool(const float *xyz, const float *new_xyz, const float *features, const int *idx, int B, int N, int m,
+                      int nsample, int C, float radius, int normalize_xyz, int use_xyz, int n_layers, const int *widths,
+                      const float *const *weights, const float *const *scales, const float *const *shifts, int pool_avg,
+                      float *out, void *stream);
+
 /* ---- fused hot path: FPS -> kNN -> geodesic -------------------------------------------------- */
 
 /* Device-resident scene: xyz (N,3) -> seeds (Q) i32, geo (Q,N) f32.  knn_dist / knn_idx32 (N,k)

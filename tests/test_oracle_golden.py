@@ -253,3 +253,32 @@ def test_attention_oracle_matches_reference_layer_fixture():
         w = {k: T(g["c%d_%s" % (i, k)]) for k in ("w1", "b1", "w2", "b2", "wv", "bv", "wo", "bo")}
         out = oatt.rel_cross_attention(T(g["c%d_tgt2" % i]), T(g["c%d_memory" % i]), T(g["c%d_rel" % i]), w)
         np.testing.assert_allclose(out.numpy(), g["c%d_out" % i], rtol=1e-5, atol=1e-6)
+
+
+def _aggregate_case(g, i):
+    import torch
+
+    T = lambda a: torch.from_numpy(np.array(a))  # noqa: E731
+    layers = []
+    l = 0
+    while "c%d_w%d" % (i, l) in g.files:
+        layers.append({"w": T(g["c%d_w%d" % (i, l)]), "gamma": T(g["c%d_gamma%d" % (i, l)]), "beta": T(g["c%d_beta%d" % (i, l)]),
+                       "mean": T(g["c%d_mean%d" % (i, l)]), "var": T(g["c%d_var%d" % (i, l)])})
+        l += 1
+    radius, ns, norm = g["c%d_meta" % i]
+    xyz, feats, inds = T(g["c%d_xyz" % i]), T(g["c%d_feats" % i]), T(g["c%d_inds" % i])
+    new_xyz = torch.stack([xyz[b][inds[b].long()] for b in range(xyz.shape[0])])
+    return xyz, new_xyz, feats, T(g["c%d_idx" % i]), float(radius), bool(norm), layers
+
+
+def test_aggregate_oracle_matches_reference_module_fixture():
+    """oracle/aggregate.py against tests/golden/aggregate_golden.npz = what the reference's OWN
+    PointnetSAModuleVotesSeparate.mlp returns on CPU (tests/golden/make_golden_aggregate.py)"""
+    from oracle import aggregate as oagg
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aggregate_golden.npz"))
+    for i in range(int(g["n"])):
+        xyz, new_xyz, feats, idx, radius, norm, layers = _aggregate_case(g, i)
+        for pooling in ("max", "avg"):
+            out = oagg.group_mlp_pool(xyz, new_xyz, feats, idx, radius, norm, True, layers, pooling=pooling)
+            np.testing.assert_allclose(out.numpy(), g["c%d_%s" % (i, pooling)], rtol=1e-5, atol=1e-6)
