@@ -738,6 +738,47 @@ def extra_records(args, cfg, xs, dev, stream, peak):
             except Exception as ex:
                 out[name] = {"error": repr(ex)}
 
+    # ---- config 5: the post-backbone few-shot forward (stub backbone, random weights) with the library's kernels vs
+    #      the reference's torch formulation of the same pieces, at the model's shapes --------------------------------
+    if args.workload == "c2":
+        try:
+            from geoformer_b200.harness import FewShotForward
+
+            torch.manual_seed(5)
+            net = FewShotForward().to(dev)  # m=16, dec_dim 64, 4 layers, 2048 contexts, 256 queries (test config)
+            locs = xs[0][None].contiguous()
+            feats = torch.randn(1, N, 16, device=dev)
+            support = torch.randn(1, 32, device=dev)
+
+            def run(impl):
+                return net(locs, feats, support, impl=impl)  # neighbor 64, radius 0.05, max_step 256 (:497-506)
+
+            def timeit_h(impl, reps=4):
+                run(impl)
+                torch.cuda.synchronize(dev)
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(stream)
+                for _ in range(reps):
+                    o = run(impl)
+                b_.record(stream)
+                torch.cuda.synchronize(dev)
+                return a_.elapsed_time(b_) / reps, o
+
+            t_b, o_b = timeit_h("b200")
+            t_t, o_t = timeit_h("torch")
+            scale = o_t[0][0].abs().max().item()
+            out["config5_harness"] = {
+                "what": "geoformer_fs.py:424-596 after the backbone (stub): aggregator -> geodesic (k=64, r=0.05, 256 levels) "
+                        "-> 4 decoder layers -> mask head, 100k foreground points, 2048 contexts, 256 queries, random init",
+                "ms_forward_b200_path": t_b, "ms_forward_torch_formulation": t_t, "speedup": t_t / t_b,
+                "mask_logit_max_abs_diff": (o_b[0][0] - o_t[0][0]).abs().max().item(), "mask_logit_scale": scale,
+                "note": "both share the geodesic maps' kernel (the reference's torch level loop needs tens of GB at this "
+                        "size) and the plain torch.nn layers; the difference is the fused aggregator, the fused "
+                        "embedding + cross-attention and the mask-head epilogue"}
+            del net, o_b, o_t
+        except Exception as ex:
+            out["config5_harness"] = {"error": repr(ex)}
+
     # ---- the two distance -> bias epilogues, timed on their own ---------------------
     try:
         from geoformer_b200.bias import decoder_relative_embedding, decoder_relative_pos, mask_head_relative_coords
