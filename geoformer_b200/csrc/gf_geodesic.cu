@@ -521,6 +521,9 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
   asm volatile("mov.u32 %0, %0;" : "+r"(vis_s));
   asm volatile("mov.u32 %0, %0;" : "+r"(fq_s));
   asm volatile("mov.u64 %0, %0;" : "+l"(claim));
+  asm volatile("mov.u64 %0, %0;" : "+l"(dist));
+  uint32_t cnt0_s = (uint32_t)__cvta_generic_to_shared(s_next_n);
+  asm volatile("mov.u32 %0, %0;" : "+r"(cnt0_s));
   unsigned char *claimb = reinterpret_cast<unsigned char *>(claim);
   auto fq_at = [&](int i) {
     int v;
@@ -682,18 +685,30 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
         // of cells): with 16-byte pieces a run fell to one lane looping 50+ times while the CTA waited at the
         // barrier, and the rows of a shell to a few warps; word by word a run spreads over neighbouring lanes and the
         // shell over all warps.
-        int *cnt = &s_next_n[level & 1];
+        // All shared accesses go through the opaque 32-bit window addresses: left to itself ptxas re-derives the
+        // generic addresses (S2R of the CTA's window, constant-bank loads) for every word, 18 instructions per test.
+        const uint32_t cnt_s = cnt0_s + 4u * (uint32_t)(level & 1);
         const int par = level & 1;
-        for (int j = tid; j < words; j += THREADS) {
-          const uint32_t c = clm[j];
+        const uint32_t jend = clm_s + 4u * (uint32_t)words, v_off = 4u * (uint32_t)words;
+        for (uint32_t ja = clm_s + 4u * tid; ja < jend; ja += 4u * THREADS) {
+          uint32_t c;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(ja) : "memory");
           if (c == 0u) continue;
-          clm[j] = 0u;
-          vis[j] |= c;
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(ja), "r"(0u) : "memory");
+          asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(ja - v_off), "r"(c) : "memory");  // this thread owns the word
           const int n = __popc(c);
-          int at = atomicAdd(cnt, n);
-          const int base = j * 32;
+          int at;
+          asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(at) : "r"(cnt_s), "r"(n) : "memory");
+          const int base = (int)((ja - clm_s) << 3);  // 32 * word index
           if (at + n <= QC) {  // the usual case: all of the word's points land in the on-chip queue
-            for (uint32_t m = c; m; m &= m - 1) fq[at++] = base + __ffs((int)m) - 1;
+            uint32_t wa = fq_s + 4u * (uint32_t)at;
+            do {  // highest bit first: one FLO per point (the order inside the frontier is immaterial)
+              uint32_t bpos;
+              asm("bfind.u32 %0, %1;" : "=r"(bpos) : "r"(c));
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(base + (int)bpos) : "memory");
+              wa += 4u;
+              c ^= 1u << bpos;
+            } while (c);
           } else {
             for (uint32_t m = c; m; m &= m - 1) {
               const int t = base + __ffs((int)m) - 1;

@@ -279,6 +279,18 @@ struct TopK {
       }
     }
   }
+  __device__ __forceinline__ void offer_key(unsigned long long kk) {
+    if (kk < key[KT - 1]) {
+      key[KT - 1] = kk;
+#pragma unroll
+      for (int i = KT - 1; i > 0; --i) {
+        unsigned long long a = key[i - 1], b = key[i];
+        bool sw = b < a;
+        key[i - 1] = sw ? b : a;
+        key[i] = sw ? a : b;
+      }
+    }
+  }
   __device__ __forceinline__ float kth_d2() const { return __uint_as_float((unsigned)(key[KT - 1] >> 32)); }
   // The row of the propagation's edge table (gf_geodesic.cu: geo_pack_edges_kernel, same rule): neighbour
   // 1 + e of the result as edge e if it may ever be used (sqrt(d2) <= radius, geodesic_utils.py:123,151),
@@ -437,6 +449,138 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ---- grid query, warp-synchronous insertion --------------------------------------------------------
+// The kernel above spends its instructions on DIVERGENT insertions: a lane inserts at ~56 of its ~195 candidates
+// (k (1 + ln(n/k))), but the 32 lanes of a warp insert at different candidates, so the warp executes the
+// insertion network at nearly every candidate (12 of 32 lanes active on average).  Here a candidate that beats the
+// lane's current k-th key is only PUSHED onto a small per-lane stack in shared memory; the warp runs the
+// insertion network when some lane's stack is nearly full, and then every lane with a pending key inserts one
+// (LIFO: the order of insertions does not change the final set, keys are distinct; a key that no longer beats
+// the k-th is dropped at the pop).  ~85 executions of the network per warp instead of ~200, each at ~25 lanes.
+// Control flow is warp-uniform (votes), every lane walks its own sequence of candidate ranges and never idles
+// before its shell is exhausted; the per-shell termination test is unchanged (after draining the stacks).
+constexpr int KNN_PEND = 8;  // stack depth; a step pushes at most 4, the network runs while a stack holds > 4
+#ifndef KNN_SYNC_MIN_BLOCKS
+#define KNN_SYNC_MIN_BLOCKS 1
+#endif
+template <int KT>
+__global__ void __launch_bounds__(128, KT <= 16 ? KNN_SYNC_MIN_BLOCKS : 1)
+    knn_grid_query_sync_kernel(const KnnGrid *__restrict__ gp, const float4 *__restrict__ sorted,
+                               const int *__restrict__ start, const float *__restrict__ queries, int nq, int k,
+                               int do_sqrt, float *__restrict__ dist, long long *__restrict__ idx64,
+                               int *__restrict__ idx32, const KnnEdgeOut eo) {
+  __shared__ unsigned long long pend[KNN_PEND][128];
+  constexpr unsigned FULL = 0xffffffffu;
+  const KnnGrid g = *gp;
+  const int tid = threadIdx.x;
+  const int s = blockIdx.x * blockDim.x + tid;
+  const bool live = s < nq;
+  if (eo.tgt && s == 0) {  // the sentinel row N: only edges to N
+    const int none = eo.rank ? (int)((((unsigned)nq >> 5) << 7) | ((unsigned)nq & 31u)) : nq;
+    for (int e = 0; e < (1 << eo.slot_bits); ++e)
+      eo.tgt[((size_t)nq << eo.slot_bits) + e] = none, eo.len[((size_t)nq << eo.slot_bits) + e] = 0.f;
+  }
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  int row = 0;
+  if (live) {
+    if (queries == nullptr) {
+      float4 me = sorted[s];
+      qx = me.x, qy = me.y, qz = me.z;
+      row = __float_as_int(me.w);
+    } else {
+      qx = __ldg(queries + (size_t)s * 3), qy = __ldg(queries + (size_t)s * 3 + 1), qz = __ldg(queries + (size_t)s * 3 + 2);
+      row = s;
+    }
+  }
+  const int cx = cell_coord(qx, g.ox, g.inv_h, g.dx), cy = cell_coord(qy, g.oy, g.inv_h, g.dy),
+            cz = cell_coord(qz, g.oz, g.inv_h, g.dz);
+  TopK<KT> top;
+  top.init(k);
+  int npend = 0;
+  auto insert_round = [&]() {  // every lane with a pending key inserts its newest one
+    if (npend > 0) top.offer_key(pend[--npend][tid]);
+  };
+  const int rmax = max(g.dx, max(g.dy, g.dz));
+  bool active = live;
+  for (int R = 0; R <= rmax; ++R) {
+    if (!__any_sync(FULL, active)) break;
+    const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dz - 1);
+    const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dy - 1);
+    const int xl = cx - R, xr = cx + R;
+    // this lane's walk over the candidate ranges of shell R: rows (z, y) of the block; on a face of the shell the
+    // whole x-run belongs to it (one range), otherwise only its two end cells (two ranges)
+    int z = z0, y = y0, sg = 0, p = 0, p1 = 0;
+    bool more = active;
+    for (;;) {
+      if (more && p >= p1) {
+        for (;;) {
+          if (z > z1) {
+            more = false;
+            break;
+          }
+          const bool face = R == 0 || z == cz - R || z == cz + R || y == cy - R || y == cy + R;
+          const int rowbase = (z * g.dy + y) * g.dx;
+          int xa, xb;
+          bool last;
+          if (face)
+            xa = max(xl, 0), xb = min(xr, g.dx - 1), last = true;
+          else
+            xa = xb = sg == 0 ? xl : xr, last = sg == 1;
+          if (last) {
+            sg = 0;
+            if (++y > y1) y = y0, ++z;
+          } else {
+            sg = 1;
+          }
+          if (xa < 0 || xb >= g.dx || xa > xb) continue;
+          p = __ldg(start + rowbase + xa), p1 = __ldg(start + rowbase + xb + 1);
+          if (p < p1) break;
+        }
+      }
+      if (!__any_sync(FULL, more)) break;
+      if (more) {  // up to four candidates of this lane's current range
+        const int n = min(p1 - p, 4);
+        float4 c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (u < n) c[u] = __ldg(sorted + p + u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (u < n) {
+            const float d2 = sq3(c[u].x - qx, c[u].y - qy, c[u].z - qz);
+            const unsigned long long kk = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(c[u].w);
+            if (kk < top.key[KT - 1]) pend[npend++][tid] = kk;
+          }
+        p += 4;
+      }
+      while (__any_sync(FULL, npend > KNN_PEND - 4)) insert_round();
+    }
+    while (__any_sync(FULL, npend > 0)) insert_round();
+    if (active) {
+      // distance from the query to the nearest face of the visited block that still has cells
+      // behind it; every unvisited point is at least that far away (minus the fp32 slack)
+      float mfd = __int_as_float(0x7f800000);
+      if (cx - R > 0) mfd = fminf(mfd, qx - (g.ox + (float)(cx - R) * g.h));
+      if (cx + R + 1 < g.dx) mfd = fminf(mfd, (g.ox + (float)(cx + R + 1) * g.h) - qx);
+      if (cy - R > 0) mfd = fminf(mfd, qy - (g.oy + (float)(cy - R) * g.h));
+      if (cy + R + 1 < g.dy) mfd = fminf(mfd, (g.oy + (float)(cy + R + 1) * g.h) - qy);
+      if (cz - R > 0) mfd = fminf(mfd, qz - (g.oz + (float)(cz - R) * g.h));
+      if (cz + R + 1 < g.dz) mfd = fminf(mfd, (g.oz + (float)(cz + R + 1) * g.h) - qz);
+      if (mfd == __int_as_float(0x7f800000)) active = false;  // the whole grid has been visited
+      const float ms = mfd - g.slack;
+      if (ms > 0.f && top.kth_d2() < ms * ms) active = false;
+    }
+  }
+  if (!live) return;
+  if (dist || idx64 || idx32)
+    top.store(k, do_sqrt != 0, dist ? dist + (size_t)row * k : nullptr, idx64 ? idx64 + (size_t)row * k : nullptr,
+              idx32 ? idx32 + (size_t)row * k : nullptr);
+  if (eo.tgt) {  // self query only (nq == N): the propagation's edge rows, written straight from the registers
+    const size_t er = (size_t)(eo.rank ? s : row) << eo.slot_bits;  // cell-order row (= this thread) or original row
+    top.store_edges(k, eo.radius, nq, eo.slot_bits, eo.rank, eo.tgt + er, eo.len + er);
+  }
+}
+
 // ---- brute force (algo 1) -----------------------------------------------------------------------
 constexpr int BF_TILE = 1024;
 template <int KT>
@@ -499,8 +643,16 @@ template <int KT>
 static void launch_grid_query(const KnnGrid *g, const float4 *sorted, const int *start, const float *queries, int nq,
                               int k, int do_sqrt, float *dist, long long *i64, int *i32, const KnnEdgeOut &eo,
                               cudaStream_t st) {
-  knn_grid_query_kernel<KT><<<(nq + 127) / 128, 128, 0, st>>>(g, sorted, start, queries, nq, k, do_sqrt, dist, i64, i32,
-                                                              eo);
+  static const bool sync = [] {  // GF_KNN_SYNC=0: the divergent-insertion kernel (kept for A/B and as a second opinion)
+    const char *e = getenv("GF_KNN_SYNC");
+    return !(e && e[0] == '0');
+  }();
+  if (sync)
+    knn_grid_query_sync_kernel<KT><<<(nq + 127) / 128, 128, 0, st>>>(g, sorted, start, queries, nq, k, do_sqrt, dist, i64,
+                                                                     i32, eo);
+  else
+    knn_grid_query_kernel<KT><<<(nq + 127) / 128, 128, 0, st>>>(g, sorted, start, queries, nq, k, do_sqrt, dist, i64, i32,
+                                                                eo);
 }
 template <int KT>
 static void launch_brute(const float *xyz, int N, const float *queries, int nq, int k, int do_sqrt, float *dist,
