@@ -432,11 +432,14 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
 //  * CELL ORDER.  The propagation runs on the kNN grid's cell-order numbering of the points (rank / order of
 //    gf_knn.cu: points of a cell are consecutive, cells of a row adjacent), so a frontier -- a shell in space --
 //    touches a few dense runs of ids instead of N/8 random sectors.
-//  * CLAIMS AND DISTANCES IN PER-CTA SCRATCH, not in the output row: claim[t] (32-bit key, RED.MIN) and dist[t]
-//    are indexed by cell-order id, so a seed touches ~13 % of their sectors (its reach) and they stay in L2.  A
-//    claim entry is reset by the thread that resolves it, so the array is cleared once per CTA, not per seed.
+//  * CLAIMS AND DISTANCES IN PER-CTA SCRATCH, not in the output row, and in ONE array indexed by cell-order id.
+//    An entry is either a claim key of the running seed (< 2^31: order << slot_bits | slot, RED.MIN) or, with the
+//    top bit set, a distance (the sign bit is spare, distances are >= 0) -- of the running seed if the point is
+//    visited, else a leftover of an earlier seed of this CTA, which loses against every key.  So nothing is ever
+//    reset: the array is cleared once per CTA, a resolve replaces the key by the distance, the final pass only
+//    reads.  A seed touches ~13 % of the sectors (its reach) and they stay in L2.
 //  * THE OUTPUT ROW IS WRITTEN ONCE, streaming, after the seed's last level: out[i] = visited(rank[i]) ?
-//    dist[rank[i]] : -1 (geodesic_utils.py:113 fills with -1 first; same result).  No read-modify-write of the
+//    distance(rank[i]) : -1 (geodesic_utils.py:113 fills with -1 first; same result).  No read-modify-write of the
 //    402 MB/s-per-scene matrix, DRAM traffic = the matrix itself.
 //  * The tie rule needs the ORIGINAL parent index (smallest parent index, then slot, wins): keys are
 //    order[p] << slot_bits | slot; resolving maps the winner back through rank[].
@@ -446,6 +449,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
 //  * Edge targets are stored ENCODED (see geo_claim4_enc) so that the visited test is four instructions.
 constexpr int GEO_MAXB = 16;  // scenes per launch (descriptors travel in the kernel parameters)
 constexpr uint32_t GEO_UNCLAIMED = 0xFFFFFFFFu;
+constexpr uint32_t GEO_DISTANCE = 0x80000000u;  // entries >= this are distances (or never touched), below: claim keys
 
 struct GeoScene {
   const int *tgt;             // (N + 1, KP) encoded edge targets, rows and targets in cell order
@@ -461,8 +465,7 @@ struct GeoBatchArgs {
   GeoScene sc[GEO_MAXB];
   int B, total_items, max_step, slot_bits, qcap;
   int *overflow;    // per CTA: ovf_stride frontier entries beyond the on-chip queue
-  uint32_t *claim;  // per CTA: arr_stride claim keys
-  float *dist;      // per CTA: arr_stride distances
+  uint32_t *claim;  // per CTA: arr_stride entries: winning key (< 2^31) | 0x80000000 + distance bits
   size_t ovf_stride, arr_stride;
   unsigned *item_counter;
 #ifdef GF_TRACE
@@ -509,8 +512,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
   const uint32_t keysub = sub << 2;
   int *ovf = a.overflow + (size_t)blockIdx.x * a.ovf_stride;
   uint32_t *claim = a.claim + (size_t)blockIdx.x * a.arr_stride;
-  float *dist = a.dist + (size_t)blockIdx.x * a.arr_stride;
-  {  // all claim entries start unclaimed; afterwards every entry is reset by the thread that resolves it
+  {  // once per CTA: no entry may look like a claim key; afterwards every key is replaced by a distance when resolved
     uint4 *c4 = reinterpret_cast<uint4 *>(claim);
     const uint4 ff = make_uint4(GEO_UNCLAIMED, GEO_UNCLAIMED, GEO_UNCLAIMED, GEO_UNCLAIMED);
     for (size_t i = tid; i < a.arr_stride / 4; i += THREADS) c4[i] = ff;
@@ -521,7 +523,6 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
   asm volatile("mov.u32 %0, %0;" : "+r"(vis_s));
   asm volatile("mov.u32 %0, %0;" : "+r"(fq_s));
   asm volatile("mov.u64 %0, %0;" : "+l"(claim));
-  asm volatile("mov.u64 %0, %0;" : "+l"(dist));
   uint32_t cnt0_s = (uint32_t)__cvta_generic_to_shared(s_next_n);
   asm volatile("mov.u32 %0, %0;" : "+r"(cnt0_s));
   unsigned char *claimb = reinterpret_cast<unsigned char *>(claim);
@@ -577,12 +578,11 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
     // level 1: the distance is the edge itself (:127); later: edge + parent's distance (:139,:144)
     auto resolve = [&](int t, int won) {
       const uint32_t key = ld_cg_u32(claim + t);
-      claim[t] = GEO_UNCLAIMED;
       const unsigned po = key >> sb, j = key & (KP - 1);
       const unsigned p = rank ? (unsigned)__ldg(rank + po) : po;
       const float w = __ldg(S.len + ((size_t)p << sb) + j);
-      const float d = won == 1 ? w : __fadd_rn(w, __ldcg(dist + p));
-      dist[t] = d;
+      const float d = won == 1 ? w : __fadd_rn(w, __uint_as_float(ld_cg_u32(claim + p) & 0x7FFFFFFFu));
+      claim[t] = __float_as_uint(d) | GEO_DISTANCE;
       rmax = fmaxf(rmax, d);
     };
 #ifdef GF_TRACE
@@ -648,7 +648,6 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
 #pragma unroll
         for (int u = 0; u < 2; ++u)
           if (rt[u] >= 0) {
-            claim[rt[u]] = GEO_UNCLAIMED;
             const unsigned po = rkey[u] >> sb;
             rp[u] = rank ? (unsigned)__ldg(rank + po) : po;
           }
@@ -656,14 +655,14 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
         for (int u = 0; u < 2; ++u)
           if (rt[u] >= 0) {
             rw[u] = __ldg(S.len + ((size_t)rp[u] << sb) + (rkey[u] & (KP - 1)));
-            if (level > 2) rpd[u] = __ldcg(dist + rp[u]);
+            if (level > 2) rpd[u] = __uint_as_float(ld_cg_u32(claim + rp[u]) & 0x7FFFFFFFu);
           }
         for (int i = (int)tid + 2 * THREADS; i < F; i += THREADS) resolve(frontier(i, (level - 1) & 1), level - 1);
 #pragma unroll
         for (int u = 0; u < 2; ++u)
           if (rt[u] >= 0) {
             const float d = level == 2 ? rw[u] : __fadd_rn(rw[u], rpd[u]);
-            dist[rt[u]] = d;
+            claim[rt[u]] = __float_as_uint(d) | GEO_DISTANCE;
             rmax = fmaxf(rmax, d);
           }
       }
@@ -675,7 +674,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
       if (level == 1 && seed_ok && tid == (((unsigned)s >> 5) & (THREADS - 1))) {  // the owner of the seed's word
         // the seed joins the visited set now; if no self edge re-won it, its distance stays 0
         // (a re-won seed holds its key until it is resolved with the other level-1 points)
-        if (ld_cg_u32(claim + s) == GEO_UNCLAIMED) dist[s] = 0.f;
+        if (ld_cg_u32(claim + s) >= GEO_DISTANCE) claim[s] = GEO_DISTANCE;  // no key: distance 0
         vis[(unsigned)s >> 5] |= 1u << (s & 31);
       }
       {
@@ -736,16 +735,16 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
     if (level >= 1)
       for (int i = tid; i < F; i += THREADS) resolve(frontier(i, level & 1), level);
     if (level == 0 && seed_ok && tid == 0) {  // max_step <= 0: only the seed entry (:118)
-      dist[s] = 0.f;
+      claim[s] = GEO_DISTANCE;  // distance 0
       vis[(unsigned)s >> 5] |= 1u << (s & 31);
     }
-    __syncthreads();  // every distance of the seed is in dist[], every reached point in the visited bitmap
-    {  // ---- the output row, written once: out[i] = visited(rank[i]) ? dist[rank[i]] : -1 (:113) ----------------
+    __syncthreads();  // every reached point is in the visited bitmap and its entry holds its distance
+    {  // ---- the output row, written once: out[i] = visited(rank[i]) ? distance(rank[i]) : -1 (:113) ------------
       float *row = S.geo + (size_t)q * N;
       auto value = [&](int r) {
         uint32_t w;
         asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(vis_s + (((unsigned)r >> 3) & ~3u)));
-        return (w >> (r & 31)) & 1u ? __ldcg(dist + r) : -1.f;
+        return (w >> (r & 31)) & 1u ? __uint_as_float(__ldcg(claim + r) & 0x7FFFFFFFu) : -1.f;
       };
       if ((((uintptr_t)row) & 15) == 0) {
         const int nvec = N >> 2;
@@ -866,7 +865,7 @@ static bool geo_batchable(int maxN) {
 }
 
 static void plan_batch(int maxN, long long items, GeoBatchPlan *p) {
-  static const int force_threads = env_int("GF_GEO_THREADS", 0), unroll = env_int("GF_GEO_UNROLL", 2),
+  static const int force_threads = env_int("GF_GEO_THREADS", 0), unroll = env_int("GF_GEO_UNROLL", 1),
                    bps_cap = env_int("GF_GEO_BPS", 0), many_threads = env_int("GF_GEO_BATCH_THREADS", 512);
   const int sms = num_sms();
   p->words = geo_bitmap_words(maxN);
@@ -894,7 +893,7 @@ static void plan_batch(int maxN, long long items, GeoBatchPlan *p) {
   p->ovf_stride = (size_t)maxN + 2;
   p->arr_stride = ((size_t)maxN + 1 + 3) & ~(size_t)3;  // claim keys / distances per CTA, whole 16-byte pieces
   long long grid = (long long)sms * best_fit;
-  const long long ovf_cap = (long long)(GEO_SCRATCH_BUDGET / (sizeof(int) * (p->ovf_stride + 2 * p->arr_stride)));
+  const long long ovf_cap = (long long)(GEO_SCRATCH_BUDGET / (sizeof(int) * (p->ovf_stride + p->arr_stride)));
   if (grid > ovf_cap) grid = ovf_cap > sms ? ovf_cap : sms;
   if (grid > items) grid = items;
   p->grid = (int)(grid < 1 ? 1 : grid);
@@ -908,7 +907,7 @@ static size_t geo_edge_bytes(int N, int k) {
 size_t geodesic_batch_scratch_bytes(int maxN, long long items) {
   GeoBatchPlan p;
   plan_batch(maxN, items, &p);
-  return align256(sizeof(int) * p.ovf_stride * (size_t)p.grid) + 2 * align256(sizeof(int) * p.arr_stride * (size_t)p.grid) +
+  return align256(sizeof(int) * p.ovf_stride * (size_t)p.grid) + align256(sizeof(int) * p.arr_stride * (size_t)p.grid) +
          align256(256) + 1024;
 }
 
@@ -1027,8 +1026,8 @@ int geodesic_batch_launch(const GeoSceneDesc *scenes, int B, int k, int max_step
   const int slot_bits = geo_slot_bits(k);
   for (int b = 0; b < B; ++b) {
     const GeoSceneDesc &d = scenes[b];
-    if ((((unsigned long long)d.N + 1) << slot_bits) >= 0xFFFFFFFFull) {
-      set_error("geodesic: N=%d with k=%d does not fit the 32-bit claim key", d.N, k);
+    if ((((unsigned long long)d.N + 1) << slot_bits) >= 0x80000000ull) {
+      set_error("geodesic: N=%d with k=%d does not fit the 31-bit claim key", d.N, k);
       return GF_ERR_INVALID;
     }
     GeoScene &s = ga.sc[b];
@@ -1053,7 +1052,6 @@ int geodesic_batch_launch(const GeoSceneDesc *scenes, int B, int k, int max_step
   Arena a(scratch, scratch_bytes);
   ga.overflow = a.take<int>(p.ovf_stride * (size_t)p.grid);
   ga.claim = a.take<uint32_t>(p.arr_stride * (size_t)p.grid);
-  ga.dist = a.take<float>(p.arr_stride * (size_t)p.grid);
   ga.item_counter = a.take<unsigned>(64);
   if (!a.ok) {
     set_error("geodesic: scratch too small (%zu bytes given, %zu needed)", scratch_bytes,
@@ -1141,7 +1139,6 @@ int geodesic_run(const float *D, const void *I, int is64, int N, int k, const in
     plan_batch(N, Q, &p);
     (void)a.take<int>(p.ovf_stride * (size_t)p.grid);
     (void)a.take<uint32_t>(p.arr_stride * (size_t)p.grid);
-    (void)a.take<float>(p.arr_stride * (size_t)p.grid);
     unsigned *ctl = a.take<unsigned>(64);
     unsigned long long *stats = (unsigned long long *)(ctl + 32);  // second half of the 256-byte control block
     GeoSceneDesc d;

@@ -643,10 +643,15 @@ template <int KT>
 static void launch_grid_query(const KnnGrid *g, const float4 *sorted, const int *start, const float *queries, int nq,
                               int k, int do_sqrt, float *dist, long long *i64, int *i32, const KnnEdgeOut &eo,
                               cudaStream_t st) {
-  static const bool sync = [] {  // GF_KNN_SYNC=0: the divergent-insertion kernel (kept for A/B and as a second opinion)
+  // GF_KNN_SYNC=0|1 forces one kernel for every k.  Measured (c2, B200): the two execute the same number of warp
+  // instructions at k = 16 (the saved insertions are spent on votes and the divergent range walk) and the
+  // synchronous one is 10 % slower alone, 1 % slower in the batched pipeline; at k = 64, where an insertion is 64
+  // compare-exchanges, it is 10-16 % faster.
+  static const int force = [] {
     const char *e = getenv("GF_KNN_SYNC");
-    return !(e && e[0] == '0');
+    return e ? (e[0] == '0' ? 0 : 1) : -1;
   }();
+  const bool sync = force >= 0 ? force == 1 : KT > 32;
   if (sync)
     knn_grid_query_sync_kernel<KT><<<(nq + 127) / 128, 128, 0, st>>>(g, sorted, start, queries, nq, k, do_sqrt, dist, i64,
                                                                      i32, eo);
