@@ -269,6 +269,7 @@ struct TopK {
   __device__ __forceinline__ void offer(float d2, int index) {
     unsigned long long kk = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)index;
     if (kk < key[KT - 1]) {
+#ifdef KNN_SERIAL_INSERT
       key[KT - 1] = kk;
 #pragma unroll
       for (int i = KT - 1; i > 0; --i) {
@@ -277,18 +278,31 @@ struct TopK {
         key[i - 1] = sw ? b : a;
         key[i] = sw ? a : b;
       }
+#else
+      // every slot decides for itself (no compare-exchange chain through the moving key): slot i takes its lower
+      // neighbour if the new key sorts below that one, the new key if it sorts below the slot's own key, else it
+      // keeps what it has; top down, so a slot's lower neighbour is still the old one when it is read
+      bool below = true;  // kk < key[KT - 1]
+#pragma unroll
+      for (int i = KT - 1; i > 0; --i) {
+        const bool below_prev = kk < key[i - 1];
+        key[i] = below_prev ? key[i - 1] : (below ? kk : key[i]);
+        below = below_prev;
+      }
+      if (below) key[0] = kk;
+#endif
     }
   }
   __device__ __forceinline__ void offer_key(unsigned long long kk) {
     if (kk < key[KT - 1]) {
-      key[KT - 1] = kk;
+      bool below = true;
 #pragma unroll
       for (int i = KT - 1; i > 0; --i) {
-        unsigned long long a = key[i - 1], b = key[i];
-        bool sw = b < a;
-        key[i - 1] = sw ? b : a;
-        key[i] = sw ? a : b;
+        const bool below_prev = kk < key[i - 1];
+        key[i] = below_prev ? key[i - 1] : (below ? kk : key[i]);
+        below = below_prev;
       }
+      if (below) key[0] = kk;
     }
   }
   __device__ __forceinline__ float kth_d2() const { return __uint_as_float((unsigned)(key[KT - 1] >> 32)); }
