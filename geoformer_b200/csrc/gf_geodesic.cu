@@ -546,7 +546,6 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) geo_bfs_batch_kernel(
     // (F_L + F_{L+1} <= N + 1), so one buffer of N + 2 entries serves both, odd levels from the bottom, even from the top
     auto ovf_at = [&](int i, int parity) { return parity ? (size_t)(i - QC) : (size_t)N + 1 - (size_t)(i - QC); };
     auto frontier = [&](int i, int parity) { return i < QC ? fq_at(i) : ovf[ovf_at(i, parity)]; };
-    uint32_t *clm = vis + words;
     uint32_t clm_s = vis_s + 4u * (uint32_t)words;
     asm volatile("mov.u32 %0, %0;" : "+r"(clm_s));
     const int4 *__restrict__ trow = reinterpret_cast<const int4 *>(S.tgt) + sub;  // + (p << lsb)
