@@ -401,43 +401,67 @@ __global__ void __launch_bounds__(128)
   TopK<KT> top;
   top.init(k);
   const int rmax = max(g.dx, max(g.dy, g.dz));
+#ifndef KNN_PLAIN_ROW_ORDER
+  // distances from the query to the faces of its own cell: lower bounds for everything beyond them
+  const float gzl = qz - (g.oz + (float)cz * g.h), gzh = (g.oz + (float)(cz + 1) * g.h) - qz;
+  const float gyl = qy - (g.oy + (float)cy * g.h), gyh = (g.oy + (float)(cy + 1) * g.h) - qy;
+#endif
   for (int R = 0; R <= rmax; ++R) {
-    const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dz - 1);
-    const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dy - 1);
     const int xl = cx - R, xr = cx + R;
-    for (int z = z0; z <= z1; ++z) {
-      const bool zface = (z == cz - R) || (z == cz + R);
-      for (int y = y0; y <= y1; ++y) {
-        const bool face = zface || (y == cy - R) || (y == cy + R);
-        const int rowbase = (z * g.dy + y) * g.dx;
-        // on a face of the shell the whole x-run belongs to it; otherwise only its two end cells
-        const int nseg = (face || R == 0) ? 1 : 2;
-        for (int sgi = 0; sgi < nseg; ++sgi) {
-          int xa, xb;
-          if (nseg == 1) {
-            xa = max(xl, 0), xb = min(xr, g.dx - 1);
-          } else {
-            xa = xb = sgi == 0 ? xl : xr;
-            if (xa < 0 || xa >= g.dx) continue;
-          }
-          if (xa > xb) continue;
-          const int p0 = __ldg(start + rowbase + xa), p1 = __ldg(start + rowbase + xb + 1);
-          int p = p0;
-          for (; p + 4 <= p1; p += 4) {  // four candidates in flight: the loads and distances overlap the offers
-            const float4 c0 = __ldg(sorted + p), c1 = __ldg(sorted + p + 1), c2 = __ldg(sorted + p + 2),
-                         c3 = __ldg(sorted + p + 3);
-            const float e0 = sq3(c0.x - qx, c0.y - qy, c0.z - qz), e1 = sq3(c1.x - qx, c1.y - qy, c1.z - qz),
-                        e2 = sq3(c2.x - qx, c2.y - qy, c2.z - qz), e3 = sq3(c3.x - qx, c3.y - qy, c3.z - qz);
-            top.offer(e0, __float_as_int(c0.w));
-            top.offer(e1, __float_as_int(c1.w));
-            top.offer(e2, __float_as_int(c2.w));
-            top.offer(e3, __float_as_int(c3.w));
-          }
-          for (; p < p1; ++p) {
-            float4 c = __ldg(sorted + p);
-            float d2 = sq3(c.x - qx, c.y - qy, c.z - qz);
-            top.offer(d2, __float_as_int(c.w));
-          }
+    const int side = 2 * R + 1, nrows = side * side;
+    for (int ri = 0; ri < nrows; ++ri) {
+      // rows (dz, dy) of the shell.  R = 1 (where nearly all the work is): nearest rows first -- the row of the
+      // query's own cells, the four rows sharing a face with it, the four diagonal ones -- so that the k-th key is
+      // tight before the far cells are scanned, and a row whose slab lies beyond the current k-th distance is skipped.
+      int dz, dy;
+#ifndef KNN_PLAIN_ROW_ORDER
+      if (R == 1) {
+        // ri: 0 -> (0,0); 1..4 -> (0,-1) (0,1) (-1,0) (1,0); 5..8 -> (-1,-1) (-1,1) (1,-1) (1,1)
+        dz = (int)((0x28215u >> (2 * ri)) & 3u) - 1;  // 2-bit codes of dz + 1, ri = 0 in the low bits
+        dy = (int)((0x22161u >> (2 * ri)) & 3u) - 1;
+      } else
+#endif
+      {
+        dz = ri / side - R, dy = ri % side - R;
+      }
+      const int z = cz + dz, y = cy + dy;
+      if (z < 0 || z >= g.dz || y < 0 || y >= g.dy) continue;
+#ifndef KNN_PLAIN_ROW_ORDER
+      if (R == 1) {  // every point of the row is at least (gap_z, gap_y) away from the query
+        const float gz = dz < 0 ? gzl : (dz > 0 ? gzh : 0.f), gy = dy < 0 ? gyl : (dy > 0 ? gyh : 0.f);
+        const float bz = fmaxf(gz - g.slack, 0.f), by = fmaxf(gy - g.slack, 0.f);
+        if (bz * bz + by * by > top.kth_d2()) continue;  // (trimming the row's end cells as well: no further gain)
+      }
+#endif
+      const bool face = dz == -R || dz == R || dy == -R || dy == R;
+      const int rowbase = (z * g.dy + y) * g.dx;
+      // on a face of the shell the whole x-run belongs to it; otherwise only its two end cells
+      const int nseg = (face || R == 0) ? 1 : 2;
+      for (int sgi = 0; sgi < nseg; ++sgi) {
+        int xa, xb;
+        if (nseg == 1) {
+          xa = max(xl, 0), xb = min(xr, g.dx - 1);
+        } else {
+          xa = xb = sgi == 0 ? xl : xr;
+          if (xa < 0 || xa >= g.dx) continue;
+        }
+        if (xa > xb) continue;
+        const int p0 = __ldg(start + rowbase + xa), p1 = __ldg(start + rowbase + xb + 1);
+        int p = p0;
+        for (; p + 4 <= p1; p += 4) {  // four candidates in flight: the loads and distances overlap the offers
+          const float4 c0 = __ldg(sorted + p), c1 = __ldg(sorted + p + 1), c2 = __ldg(sorted + p + 2),
+                       c3 = __ldg(sorted + p + 3);
+          const float e0 = sq3(c0.x - qx, c0.y - qy, c0.z - qz), e1 = sq3(c1.x - qx, c1.y - qy, c1.z - qz),
+                      e2 = sq3(c2.x - qx, c2.y - qy, c2.z - qz), e3 = sq3(c3.x - qx, c3.y - qy, c3.z - qz);
+          top.offer(e0, __float_as_int(c0.w));
+          top.offer(e1, __float_as_int(c1.w));
+          top.offer(e2, __float_as_int(c2.w));
+          top.offer(e3, __float_as_int(c3.w));
+        }
+        for (; p < p1; ++p) {
+          float4 c = __ldg(sorted + p);
+          float d2 = sq3(c.x - qx, c.y - qy, c.z - qz);
+          top.offer(d2, __float_as_int(c.w));
         }
       }
     }
