@@ -318,7 +318,9 @@ def _check_geodesic(oracle_lib, dev, x, Q, k, r, ms):
 @pytest.mark.parametrize("N,Q,k,r,ms", [(400, 8, 6, 0.15, 4), (400, 8, 6, 10.0, 3), (2000, 16, 8, 0.2, 64),
                                         (3000, 32, 16, 0.5, 1), (3000, 33, 16, 0.3, 7), (20000, 64, 8, 0.5, 32),
                                         (20000, 64, 16, 0.1, 256), (20000, 300, 16, 0.5, 16),
-                                        (5000, 8, 2, 0.5, 50), (5000, 8, 1, 0.5, 50), (5000, 8, 8, 0.5, 0)])
+                                        (5000, 8, 2, 0.5, 50), (5000, 8, 1, 0.5, 50), (5000, 8, 8, 0.5, 0),
+                                        # many seeds per CTA: the claim / distance array is never reset between seeds
+                                        (3000, 2500, 8, 0.3, 12), (6000, 3000, 16, 0.25, 40)])
 def test_geodesic_matches_oracle(oracle_lib, dev, N, Q, k, r, ms):
     _check_geodesic(oracle_lib, dev, scene(N, 40 + N % 7), Q, k, r, ms)
 
