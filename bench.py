@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
     ap.add_argument("--max-step", type=int, default=None, help="override the workload's level bound")
-    ap.add_argument("--batch", type=int, default=10, help="scenes per library call (reduced to a divisor of --steps)")
+    ap.add_argument("--batch", type=int, default=20, help="scenes per library call (reduced to a divisor of --steps)")
     ap.add_argument("--repeats", type=int, default=0, help="repetitions of the K-step timed region (0 = automatic)")
     ap.add_argument("--runners", type=int, default=2, help="batches in flight (alternating CUDA streams)")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
@@ -381,7 +381,7 @@ def run_seed_sharded(args):
 
 def pick_batch(K, want):
     """largest batch size <= want that divides K (K steps must be whole calls)"""
-    for b in range(max(1, min(want, 16)), 0, -1):
+    for b in range(max(1, min(want, 32)), 0, -1):
         if K % b == 0:
             return b
     return 1

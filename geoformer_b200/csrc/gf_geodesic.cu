@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 2048 / GEO_THREADS) geo_seed_bfs_
 //    cal_geodesic_vectorize loops over the scenes of a batch, geodesic_utils.py:98), pulled from one counter by
 //    persistent CTAs: one launch, one tail per batch instead of one per scene.
 //  * Edge targets are stored ENCODED (see geo_claim4_enc) so that the visited test is four instructions.
-constexpr int GEO_MAXB = 16;  // scenes per launch (descriptors travel in the kernel parameters)
+constexpr int GEO_MAXB = 32;  // scenes per launch (descriptors travel in the kernel parameters)
 constexpr uint32_t GEO_UNCLAIMED = 0xFFFFFFFFu;
 constexpr uint32_t GEO_DISTANCE = 0x80000000u;  // entries >= this are distances (or never touched), below: claim keys
 

@@ -24,7 +24,7 @@ struct GeoSceneDesc {
 size_t geodesic_batch_scratch_bytes(int maxN, long long items);
 int geodesic_batch_launch(const GeoSceneDesc *scenes, int B, int k, int max_step, void *scratch, size_t scratch_bytes,
                           cudaStream_t st);
-constexpr int GEO_BATCH_MAX = 16;
+constexpr int GEO_BATCH_MAX = 32;
 
 // where the packed edge table of a later geodesic_run(D = nullptr, ...) on the same workspace lives
 int geodesic_edge_buffers(void *workspace, size_t workspace_bytes, int N, int k, int Q, int **tgt, float **len,

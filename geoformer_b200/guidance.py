@@ -40,7 +40,7 @@ def geodesic_guidance(xyz, n_queries, neighbor, radius, max_step, return_graph=F
     return tuple(out)
 
 
-BATCH_MAX = 16  # scenes per library call (GEO_BATCH_MAX)
+BATCH_MAX = 32  # scenes per library call (GEO_BATCH_MAX)
 BATCH_MAX_POINTS = 860_000  # beyond this a scene's bitmaps do not fit one CTA: per-scene calls
 
 
@@ -50,7 +50,7 @@ def _ptr_array(tensors):
 
 def geodesic_guidance_batch(scenes, n_queries, neighbor, radius, max_step, seeds=None, return_stats=False,
                             row_max=False, ws_tag="guidance_batch"):
-    """The hot path for a BATCH of scenes in one library call per <= 16 scenes: FPS and graph construction of the
+    """The hot path for a BATCH of scenes in one library call per <= 32 scenes: FPS and graph construction of the
     scenes side by side, ONE propagation launch over all (scene, seed) pairs (gf_guidance_batch).
     scenes: list of (N_b, 3) f32 CUDA tensors on one device.  seeds: optional list of (Q,) int tensors (then FPS is
     skipped -- the body of cal_geodesic_vectorize).  Returns (seeds list, geo list[, stats (B,2) i64][, row_max list])."""

@@ -192,7 +192,7 @@ int gf_guidance_seeded(const float *xyz, int N, const int *seeds, int Q, int k, 
  * optional row_max[b] (Q); the pointer ARRAYS live in host memory, what they point to in device memory.
  * stats: optional device (B,2) i64.  FPS and graph construction of the scenes run side by side on internal
  * streams; the propagation of ALL scenes is ONE launch whose work items are (scene, seed) pairs, so that the
- * GPU holds three to four times as many of these latency-bound runs as a scene alone offers.  B <= 16; every
+ * GPU holds three to four times as many of these latency-bound runs as a scene alone offers.  B <= 32; every
  * scene must fit the on-chip bitmaps (N <~ 860k), larger scenes go through gf_guidance one by one.          */
 size_t gf_guidance_batch_workspace_bytes(const int *Ns, int B, int Q, int k);
 int gf_guidance_batch(const float *const *xyz, const int *Ns, int B, int Q, int k, float radius, int max_step,
