@@ -571,8 +571,9 @@ def run_ours(args):
                 "kernel_ms": t_in, "kernel_ms_samples": len(prop_in_region), "kernel_ms_alone": t_alone,
                 "achieved_alone": achieved_alone, "frac_alone": (achieved_alone / peak) if achieved_alone else None,
                 "note": "kernel_ms = duration of the propagation launch (one per batch of %d scenes) between two event "
-                        "nodes of the replayed graph, inside the timed regions, where the next batch's FPS / kNN "
-                        "kernels share the SMs; *_alone = the same launch with nothing else running" % B,
+                        "nodes of the replayed graph, inside the timed regions (with more than one call per region the "
+                        "next batch's FPS / kNN kernels share the SMs); *_alone = the same launch in a call of its own"
+                        % B,
                 "compulsory_bytes_per_scene": 12.0 * N + 8.0 * N * k + 4.0 * Q * N}
 
     extras = {}
