@@ -571,8 +571,8 @@ def test_guidance_batch_equals_per_scene_calls_and_oracle(oracle_lib, dev):
         rD, rI = oracle_lib.find_knn(xn, k)
         assert np.array_equal(seeds[i].cpu().numpy(), rs)
         assert np.array_equal(geos[i].cpu().numpy(), oracle_lib.geodesic(rD, rI, rs, r, ms))
-    # seeds given (the body of cal_geodesic_vectorize), more scenes than one library call takes (16)
-    many = [xs[i % len(xs)] for i in range(19)]
+    # seeds given (the body of cal_geodesic_vectorize), more scenes than one library call takes (32): a full call + 3
+    many = [xs[i % len(xs)] for i in range(35)]
     given = [torch.randperm(x.size(0), generator=torch.Generator().manual_seed(j))[:Q].int() for j, x in enumerate(many)]
     _, geos2 = geodesic_guidance_batch(many, Q, k, r, ms, seeds=given)
     from geoformer_b200.geodesic_utils import geodesic_from_points
